@@ -1,0 +1,113 @@
+/* tetranerf_b200.h -- C ABI of the B200-native Tetra-NeRF ray-sampling hot path.
+ *
+ * Drop-in boundary: these entry points are what the reference's pybind module
+ * `tetranerf_cpp_extension` (src/py_binding.cpp:433-449) binds for this path.  Plain pointers and
+ * sizes only; every pointer named d_* is a DEVICE pointer on the tracer's device; `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  All calls are stream-ordered and
+ * asynchronous unless noted (the reference does cudaDeviceSynchronize per call,
+ * src/tetrahedra_tracer.cpp:173-174; a caller who wants that behaviour calls tn_synchronize).
+ *
+ * Return value: 0 on success, non-zero on error; tn_last_error() gives the message of the last
+ * failing call on the calling thread (the reference throws `Exception`, src/utils/exception.h:164-181,
+ * surfacing as Python RuntimeError -- the Python shim turns non-zero into RuntimeError).
+ *
+ * "E" below is 0xFFFFFFFF ("empty", -1 in the int32 tensors of the reference).
+ */
+#ifndef TETRANERF_B200_H
+#define TETRANERF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tn_tracer tn_tracer;
+
+enum { TN_OK = 0, TN_ERR_ARG = 1, TN_ERR_CUDA = 2, TN_ERR_MESH = 3, TN_ERR_STATE = 4, TN_ERR_OVERFLOW = 5 };
+
+const char *tn_last_error(void);
+int tn_version(void);
+
+/* TetrahedraTracer(device)  -- src/py_binding.cpp:30-35, src/tetrahedra_tracer.cpp:90-127 */
+int tn_create(int device, tn_tracer **out);
+/* ~TetrahedraTracer         -- src/tetrahedra_tracer.cpp:178-189 */
+int tn_destroy(tn_tracer *h);
+/* stream sync + deferred device-side error flags (traversal stack overflow) */
+int tn_synchronize(tn_tracer *h, void *stream);
+
+/* load_tetrahedra(xyz f32[V,3], cells i32[T,4]) -- src/py_binding.cpp:144-161,
+ * src/tetrahedra_tracer.cpp:244-340 (unique-face build :45-71 + acceleration structure).
+ * Borrows d_xyz / d_cells (caller keeps them alive, as the reference, tetrahedra_tracer.h:300-303).
+ * Returns TN_ERR_MESH "A triangle is shared by more than two tetrahedra!" like :64-66.
+ * Synchronous (the face table is sized on the host). */
+int tn_load_tetrahedra(tn_tracer *h, const float *d_xyz, uint32_t V, const uint32_t *d_cells, uint32_t T, void *stream);
+int tn_num_faces(tn_tracer *h, uint32_t *F);
+/* copies out the unique-face tables in reference numbering: d_tri u32[F,3], d_tt u32[F,2]
+ * (triangle_indices / triangle_tetrahedra of src/optix_types.h:4-5) */
+int tn_get_faces(tn_tracer *h, uint32_t *d_tri, uint32_t *d_tt, void *stream);
+
+/* trace_rays(origins, directions, max_ray_triangles) -- src/py_binding.cpp:41-76,
+ * src/tetrahedra_tracer.cpp:137-176, src/optix/optix_trace_rays.cu:268-331.
+ *   d_num   u32[R]        num_visited_cells
+ *   d_cells u32[R,M]      visited_cells            (tail = E)
+ *   d_bary  f32[R,M,2,3]  barycentric_coordinates  (tail = 0)
+ *   d_dist  f32[R,M,2]    hit_distances            (tail = 0)
+ *   d_verts u32[R,M,4]    vertex_indices           (tail = E)
+ * M must be a power of two (py_binding.cpp:44-47).  The kernel writes every element (no pre-zeroing
+ * needed).  dense=0 skips the tail fill (entries >= num are left untouched). */
+int tn_trace_rays(tn_tracer *h, const float *d_origins, const float *d_directions, uint32_t R, uint32_t M, uint32_t *d_num,
+                  uint32_t *d_cells, float *d_bary, float *d_dist, uint32_t *d_verts, int dense, void *stream);
+
+/* trace_rays_triangles -- src/py_binding.cpp:78-113, src/optix/optix_trace_rays_triangles.cu:49-114.
+ *   d_num u32[R], d_faces u32[R,M], d_bary f32[R,M,2], d_dist f32[R,M], d_verts u32[R,M,3]; tails 0 */
+int tn_trace_rays_triangles(tn_tracer *h, const float *d_origins, const float *d_directions, uint32_t R, uint32_t M,
+                            uint32_t *d_num, uint32_t *d_faces, float *d_bary, float *d_dist, uint32_t *d_verts, void *stream);
+
+/* find_tetrahedra(positions) -- src/py_binding.cpp:115-142, src/optix/optix_find_tetrahedra.cu:84-213.
+ *   d_tet u32[N] (E if none), d_bary f32[N,3], d_verts u32[N,4] (0 when not found) */
+int tn_find_tetrahedra(tn_tracer *h, const float *d_positions, uint32_t N, uint32_t *d_tet, float *d_bary, uint32_t *d_verts,
+                       void *stream);
+
+/* find_visited_cells -- src/py_binding.cpp:163-216, src/tetrahedra_tracer.cu:115-161.
+ * Writes every output element (defaults: cell E, verts E, mask 0, bary 0; py_binding.cpp:188-191). */
+int tn_find_visited_cells(tn_tracer *h, uint32_t R, uint32_t S, uint32_t M, const uint32_t *d_num, const uint32_t *d_cells,
+                          const float *d_bary, const float *d_dist, const uint32_t *d_verts, const float *d_sample_dist,
+                          uint32_t *d_cell_out, uint32_t *d_verts_out, uint8_t *d_mask_out, float *d_bary_out, void *stream);
+
+/* interpolate_values<D> -- src/py_binding.cpp:298-339, src/tetrahedra_tracer.cu:195-221.
+ *   d_vi u32[N,D], d_w f32[N,D-1], d_field f32[C,V] (feature-major, the checkpoint layout,
+ *   model.py:247-255), d_out f32[N,C] (contiguous; the reference returns the same values as a
+ *   moveaxis view).  D in {2,3,4,6}.  d_scratch: NULL, or >= C*V floats used for a [V,C] shadow. */
+int tn_interpolate_values(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi, const float *d_w,
+                          const float *d_field, float *d_out, float *d_scratch, void *stream);
+/* interpolate_values_backward<D> -- src/py_binding.cpp:341-372, src/tetrahedra_tracer.cu:223-248.
+ *   d_grad_in f32[N,C], d_grad_field f32[C,V] (zeroed by this call, py_binding.cpp:360). */
+int tn_interpolate_values_backward(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi,
+                                   const float *d_w, const float *d_grad_in, float *d_grad_field, void *stream);
+
+/* ---- fused forward render (new; replaces model.py:531-662 between trace_rays and the pixel) -------
+ * Weights are passed once (tn_render_set_weights) in nerfstudio state-dict layout and repacked on
+ * the device.  See DESIGN.md §"fused render". */
+typedef struct tn_render_config {
+    uint32_t max_ray_triangles; /* M, power of two                      model.py:77  */
+    uint32_t num_samples;       /* S_c                                  model.py:78  */
+    uint32_t num_fine_samples;  /* S_f (0 = single pass)                model.py:79  */
+    uint32_t use_biased_sampler;/*                                      model.py:80  */
+    float far_plane;            /* collider far plane: depth of empty rays (model.py:645-650) */
+    float background[3];        /* renderer background colour (white = 1,1,1; model.py:93) */
+} tn_render_config;
+
+/* field: f32[64,V] feature-major.  Keeps a [V,64] row-major shadow inside the tracer. */
+int tn_render_set_field(tn_tracer *h, const float *d_field, uint32_t C, uint32_t V, void *stream);
+/* mlp_base.layers.{0,1,2}.{weight,bias}, mlp_head.layers.0.{weight,bias}, field_output_color.net.*,
+ * field_output_density.net.* as 12 device pointers in that order (torch nn.Linear [out,in] layout). */
+int tn_render_set_weights(tn_tracer *h, const float *const *d_params12, void *stream);
+/* d_rgb f32[R,3], d_acc f32[R,1], d_depth f32[R,1], d_mask u8[R] */
+int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
+              float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, void *stream);
+/* number of kernels launched by this library on this tracer since creation (bench "gpu_launches") */
+uint64_t tn_launch_count(tn_tracer *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,204 @@
+// tn_ops.cu -- find_visited_cells, interpolate_values, interpolate_values_backward (stand-alone ops
+// of the pybind surface; the fused render path in tn_render.cu does the same arithmetic in-kernel).
+//
+// Replaces src/tetrahedra_tracer.cu:115-290.  Arithmetic contract with oracle/tetra_oracle.cpp:
+//   matcher : mult = (d - t_in) / (t_out - t_in)  [IEEE div],  b = (1-mult)*c1 + mult*c2 with every
+//             op individually rounded (the reference is built --use_fast_math, cmake/FindTorch.cmake:33;
+//             its result differs by a few ulp and is checked against oracle/_ref on the GPU box);
+//   interp  : out = fma(w_k, F[v_{k+1}], out) for k = 0..D-2, then fma(1 - sum(w), F[v_0], out)
+//             -- the FFMA chain nvcc emits for tetrahedra_tracer.cu:211-219.
+#include "tn_common.cuh"
+
+namespace tn {
+
+// ---- find_matched_cells (tetrahedra_tracer.cu:115-161) : literal, one thread per ray ----------
+__global__ void k_match(uint32_t R, uint32_t S, uint32_t M, const uint32_t *__restrict__ num, const uint32_t *__restrict__ cells,
+                        const float2 *__restrict__ hd, const float *__restrict__ bary, const float *__restrict__ sd,
+                        const uint4 *__restrict__ verts, uint32_t *__restrict__ cell_out, uint4 *__restrict__ verts_out,
+                        uint8_t *__restrict__ mask_out, float *__restrict__ bary_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t n = num[i];
+    const size_t row = (size_t)i * M;
+    uint32_t p = 0;
+    bool done = false;
+    for (uint32_t j = 0; j < S; ++j) {
+        const size_t g = (size_t)i * S + j;
+        uint32_t oc = TN_EMPTY;
+        uint4 ov = make_uint4(TN_EMPTY, TN_EMPTY, TN_EMPTY, TN_EMPTY);
+        uint8_t om = 0;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (!done) {
+            const float cd = sd[g];
+            while (p < n && hd[row + p].y < cd) p++;
+            if (p >= n) done = true;  // "there will be no more matches on this ray" (:137-140)
+            else {
+                const float2 h = hd[row + p];
+                if (h.x <= cd) {
+                    om = 1;
+                    oc = cells[row + p];
+                    ov = verts[row + p];
+                    const float mult = __fdiv_rn(__fsub_rn(cd, h.x), __fsub_rn(h.y, h.x));
+                    const float omm = __fsub_rn(1.0f, mult);
+                    const float *c = bary + 6 * (row + p);
+                    b0 = __fadd_rn(__fmul_rn(omm, c[0]), __fmul_rn(mult, c[3]));
+                    b1 = __fadd_rn(__fmul_rn(omm, c[1]), __fmul_rn(mult, c[4]));
+                    b2 = __fadd_rn(__fmul_rn(omm, c[2]), __fmul_rn(mult, c[5]));
+                }
+            }
+        }
+        cell_out[g] = oc; verts_out[g] = ov; mask_out[g] = om;
+        bary_out[3 * g] = b0; bary_out[3 * g + 1] = b1; bary_out[3 * g + 2] = b2;
+    }
+}
+
+// ---- [C,V] -> [V,C] ---------------------------------------------------------------------------
+__global__ void k_transpose(const float *__restrict__ in, float *__restrict__ out, uint32_t rows, uint32_t cols) {
+    __shared__ float tile[32][33];
+    const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t y = by + r, x = bx + threadIdx.x;
+        if (y < rows && x < cols) tile[r][threadIdx.x] = in[(size_t)y * cols + x];
+    }
+    __syncthreads();
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t x = bx + r, y = by + threadIdx.x;
+        if (y < rows && x < cols) out[(size_t)x * rows + y] = tile[threadIdx.x][r];
+    }
+}
+
+// ---- interpolate_values (tetrahedra_tracer.cu:195-221) ----------------------------------------
+// row-major field [V,C]: one warp per sample, lanes over features (coalesced 4C-byte vertex rows)
+template <int D>
+__global__ void k_interp_rows(uint32_t N, uint32_t C, const uint32_t *__restrict__ vi, const float *__restrict__ w,
+                              const float *__restrict__ frow, float *__restrict__ out) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= N) return;
+    uint32_t v[D];
+    float wk[D];
+    float weight = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = vi[(size_t)i * D + k];
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) { wk[k] = w[(size_t)i * (D - 1) + k]; weight = __fadd_rn(weight, wk[k]); }
+    const float w0 = __fsub_rn(1.0f, weight);
+    for (uint32_t j = lane; j < C; j += 32) {
+        float o = 0.f;
+#pragma unroll
+        for (int k = 0; k < D - 1; ++k)
+            if (v[k + 1] != TN_EMPTY) o = __fmaf_rn(wk[k], frow[(size_t)v[k + 1] * C + j], o);
+        if (v[0] != TN_EMPTY) o = __fmaf_rn(w0, frow[(size_t)v[0] * C + j], o);
+        out[(size_t)i * C + j] = o;
+    }
+}
+// feature-major field [C,V] read in place (no scratch): thread per (sample, feature)
+template <int D>
+__global__ void k_interp_cols(uint32_t N, uint32_t C, uint32_t V, const uint32_t *__restrict__ vi, const float *__restrict__ w,
+                              const float *__restrict__ field, float *__restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)N * C) return;
+    const uint32_t i = (uint32_t)(idx / C), j = (uint32_t)(idx % C);
+    float o = 0.f, weight = 0.f;
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) {
+        const float wk = w[(size_t)i * (D - 1) + k];
+        const uint32_t v = vi[(size_t)i * D + k + 1];
+        if (v != TN_EMPTY) o = __fmaf_rn(wk, field[(size_t)j * V + v], o);
+        weight = __fadd_rn(weight, wk);
+    }
+    const uint32_t v0 = vi[(size_t)i * D];
+    if (v0 != TN_EMPTY) o = __fmaf_rn(__fsub_rn(1.0f, weight), field[(size_t)j * V + v0], o);
+    out[idx] = o;
+}
+
+// ---- interpolate_values_backward (tetrahedra_tracer.cu:223-248) -------------------------------
+template <int D>
+__global__ void k_interp_bwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t *__restrict__ vi, const float *__restrict__ w,
+                             const float *__restrict__ gin, float *__restrict__ gfield) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)N * C) return;
+    const uint32_t i = (uint32_t)(idx / C), j = (uint32_t)(idx % C);
+    const float g = gin[idx];
+    float weight = 0.f;
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) {
+        const float wk = w[(size_t)i * (D - 1) + k];
+        const uint32_t v = vi[(size_t)i * D + k + 1];
+        if (v != TN_EMPTY) atomicAdd(&gfield[(size_t)j * V + v], __fmul_rn(wk, g));
+        weight = __fadd_rn(weight, wk);
+    }
+    const uint32_t v0 = vi[(size_t)i * D];
+    if (v0 != TN_EMPTY) atomicAdd(&gfield[(size_t)j * V + v0], __fmul_rn(__fsub_rn(1.0f, weight), g));
+}
+
+template <int D>
+static int interp_fwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t *vi, const float *w, const float *field, float *out,
+                      float *scratch, cudaStream_t s) {
+    if (scratch) {
+        dim3 tb(32, 8), tg((V + 31) / 32, (C + 31) / 32);
+        k_transpose<<<tg, tb, 0, s>>>(field, scratch, C, V);
+        const uint32_t threads = 256;
+        k_interp_rows<D><<<(uint32_t)(((size_t)N * 32 + threads - 1) / threads), threads, 0, s>>>(N, C, vi, w, scratch, out);
+    } else {
+        const size_t total = (size_t)N * C;
+        k_interp_cols<D><<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(N, C, V, vi, w, field, out);
+    }
+    return TN_OK;
+}
+template <int D>
+static int interp_bwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t *vi, const float *w, const float *gin, float *gfield,
+                      cudaStream_t s) {
+    const size_t total = (size_t)N * C;
+    k_interp_bwd<D><<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(N, C, V, vi, w, gin, gfield);
+    return TN_OK;
+}
+
+}  // namespace tn
+
+extern "C" int tn_find_visited_cells(tn_tracer *h, uint32_t R, uint32_t S, uint32_t M, const uint32_t *d_num, const uint32_t *d_cells,
+                                     const float *d_bary, const float *d_dist, const uint32_t *d_verts, const float *d_sample_dist,
+                                     uint32_t *d_cell_out, uint32_t *d_verts_out, uint8_t *d_mask_out, float *d_bary_out, void *stream) {
+    if (!h) return tn::fail(TN_ERR_ARG, "null tracer");
+    if (R == 0 || S == 0) return TN_OK;
+    tn::DeviceGuard g(h->device);
+    tn::k_match<<<(R + 63) / 64, 64, 0, (cudaStream_t)stream>>>(R, S, M, d_num, d_cells, (const float2 *)d_dist, d_bary, d_sample_dist,
+                                                               (const uint4 *)d_verts, d_cell_out, (uint4 *)d_verts_out, d_mask_out,
+                                                               d_bary_out);
+    h->launches += 1;
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+
+extern "C" int tn_interpolate_values(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi, const float *d_w,
+                                     const float *d_field, float *d_out, float *d_scratch, void *stream) {
+    if (N == 0 || C == 0) return TN_OK;
+    tn::DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (D) {  // py_binding.cpp:258-276
+        case 2: tn::interp_fwd<2>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
+        case 3: tn::interp_fwd<3>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
+        case 4: tn::interp_fwd<4>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
+        case 6: tn::interp_fwd<6>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
+        default: return tn::fail(TN_ERR_ARG, "Unsupported interpolation dimension with value " + std::to_string(D));
+    }
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+
+extern "C" int tn_interpolate_values_backward(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi,
+                                              const float *d_w, const float *d_grad_in, float *d_grad_field, void *stream) {
+    tn::DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    TN_CUDA(cudaMemsetAsync(d_grad_field, 0, sizeof(float) * (size_t)C * V, s));  // py_binding.cpp:360
+    if (N == 0 || C == 0) return TN_OK;
+    switch (D) {  // py_binding.cpp:278-296
+        case 2: tn::interp_bwd<2>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, s); break;
+        case 3: tn::interp_bwd<3>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, s); break;
+        case 4: tn::interp_bwd<4>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, s); break;
+        case 6: tn::interp_bwd<6>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, s); break;
+        default: return tn::fail(TN_ERR_ARG, "Unsupported interpolation dimension with value " + std::to_string(D));
+    }
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}

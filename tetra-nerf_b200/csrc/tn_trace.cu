@@ -1,0 +1,410 @@
+// tn_trace.cu -- trace_rays / trace_rays_triangles on sm_100a without OptiX.
+//
+// Replaces src/optix/optix_trace_rays.cu (+ the OptiX host runtime in src/tetrahedra_tracer.cpp:137-176,
+// 342-587).  One WARP per ray:
+//   1. all-hits gather (semantics of __anyhit__ms, optix_trace_rays.cu:310-331): the warp walks the
+//      implicit 4-ary BVH with a shared LIFO work list -- every lane pops a different node, tests its
+//      4 children, and the survivors are re-packed with a warp scan (order is irrelevant because ALL
+//      hits are wanted, so the frontier is embarrassingly parallel).  Leaves are tetrahedra; a lane
+//      tests only the faces its tetrahedron OWNS (first owner in reference numbering), so each unique
+//      face is tested once, in the reference's stored winding, by the watertight fp32 test of
+//      tn_common.cuh (bit-identical to oracle/tetra_oracle.cpp).
+//   2. hits live in shared memory as 64-bit keys (t bits << 32 | face id): a bitonic sort of the keys
+//      is the reference's bitonic_sort (optix_trace_rays.cu:78-108) with ties pinned by face id.
+//      (u,v) are not carried through the sort; they are recomputed for the <= 2 faces of each emitted
+//      record (same function, same inputs -> same bits).
+//   3. post_process_tetrahedra (optix_trace_rays.cu:110-266): if no two consecutive hits are within
+//      eps and every consecutive pair shares a tetrahedron (the generic case) the pairing is the
+//      identity and all lanes emit records in parallel; otherwise lane 0 runs the literal three-phase
+//      algorithm on the shared-memory keys and the lanes emit from its result.
+// More than M-1 hits: the M-1 smallest keys are kept (the reference keeps an arbitrary M-1).
+#include "tn_common.cuh"
+
+namespace tn {
+
+typedef unsigned long long u64;
+constexpr int TRACE_WARPS = 4;
+constexpr unsigned FULL = 0xffffffffu;
+#define TN_EPS 1e-6f  // optix_trace_rays.cu:8
+
+struct TraceParams {
+    const float *o, *d;
+    uint32_t R, M;
+    uint32_t *num, *cells;
+    float *bary, *dist;
+    uint32_t *verts;
+    const float4 *nodes;
+    const LeafRec *leaves;
+    const uint4 *tri;
+    const uint2 *tt;
+    const float *xyz;
+    BvhLevels lv;
+    float absmax;
+    int dense;
+    int *flags;
+    uint32_t hcap, scap, lcap;
+};
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ float key_t(u64 k) { return __uint_as_float((uint32_t)(k >> 32) & 0x7FFFFFFFu); }
+__device__ __forceinline__ uint32_t key_face(u64 k) { return (uint32_t)k; }
+
+// (t,u,v) of one ray/face pair, recomputed from the face's stored winding
+__device__ __forceinline__ bool face_hit(const RaySetup &rs, const float *__restrict__ xyz, const uint4 tri, float &t, float &u,
+                                         float &v) {
+    const Sheared A = shear(rs, xyz[3 * (size_t)tri.x], xyz[3 * (size_t)tri.x + 1], xyz[3 * (size_t)tri.x + 2]);
+    const Sheared B = shear(rs, xyz[3 * (size_t)tri.y], xyz[3 * (size_t)tri.y + 1], xyz[3 * (size_t)tri.y + 2]);
+    const Sheared C = shear(rs, xyz[3 * (size_t)tri.z], xyz[3 * (size_t)tri.z + 1], xyz[3 * (size_t)tri.z + 2]);
+    return tri_test(A, B, C, t, u, v);
+}
+
+// keep the `keep` smallest of hits[0..nh) (keys are distinct), compacting in place; returns the
+// largest kept key.  Rare path (ray with more than M-1 face hits).
+__device__ u64 rank_select(u64 *hits, uint32_t &nh, uint32_t keep, int lane) {
+    u64 f0 = 0, f1 = 0;
+    for (uint32_t k = 0; lane + 32 * k < nh; ++k) {
+        const u64 key = hits[lane + 32 * k];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < nh; ++j) rank += (hits[j] < key) ? 1u : 0u;
+        if (rank < keep) { if (k < 64) f0 |= 1ull << k; else f1 |= 1ull << (k - 64); }
+    }
+    __syncwarp();
+    uint32_t base = 0;
+    u64 mx = 0;
+    for (uint32_t k = 0; 32 * k < nh; ++k) {
+        const uint32_t i = lane + 32 * k;
+        const bool kp = i < nh && (((k < 64) ? (f0 >> k) : (f1 >> (k - 64))) & 1ull);
+        const u64 key = kp ? hits[i] : 0ull;
+        const uint32_t mask = __ballot_sync(FULL, kp);
+        __syncwarp();
+        if (kp) { hits[base + __popc(mask & ((1u << lane) - 1u))] = key; mx = key > mx ? key : mx; }
+        base += __popc(mask);
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const u64 t = __shfl_xor_sync(FULL, mx, o); mx = t > mx ? t : mx; }
+    nh = base;
+    return mx;
+}
+
+__device__ void bitonic_sort_keys(u64 *hits, uint32_t nh, int lane) {
+    uint32_t P = 2;
+    while (P < nh) P <<= 1;
+    for (uint32_t i = nh + lane; i < P; i += 32) hits[i] = ~0ull;
+    __syncwarp();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t idx = lane; idx < (P >> 1); idx += 32) {
+                const uint32_t i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));
+                const uint32_t ij = i | j;
+                const bool up = (i & k) == 0;
+                const u64 a = hits[i], b = hits[ij];
+                if ((a > b) == up) { hits[i] = b; hits[ij] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// literal post_process_tetrahedra (optix_trace_rays.cu:110-266) on the sorted keys; single lane.
+// key bit 63 plays hit_distances[].y (the "marked once" flag); face == TN_EMPTY plays t[j] == empty.
+// Every emitted record pairs position j with position j+1 of the array AFTER the swap of :229-235,
+// so only the list of j's is produced; the caller emits (hits[j], hits[j+1]).
+__device__ uint32_t post_process_serial(u64 *key, uint2 *tts, uint32_t n, uint16_t *emit) {
+    const u64 MARK = 1ull << 63;
+    for (uint32_t j = 0; j + 1 < n; ++j) {
+        if (key_face(key[j]) == TN_EMPTY) continue;
+        const float dn = key_t(key[j]);
+        bool clear_self = false;
+        for (uint32_t off = 1; j + off < n && (key_face(key[j + off]) == TN_EMPTY || fabsf(__fsub_rn(key_t(key[j + off]), dn)) < TN_EPS); ++off) {
+            uint32_t cell;
+            if (key_face(key[j + off]) != TN_EMPTY && common_tet(tts[j], tts[j + off], cell)) {
+                if (key_face(key[j]) != key_face(key[j + off])) clear_self = true;
+                if (key[j + off] & MARK) key[j + off] |= 0xFFFFFFFFull;  // already marked once -> delete
+                else key[j + off] |= MARK;
+            }
+        }
+        if (clear_self && (key[j] & MARK)) key[j] |= 0xFFFFFFFFull;
+        key[j] &= ~MARK;
+    }
+    uint32_t jc = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+        if (key_face(key[j]) == TN_EMPTY) continue;
+        const uint2 orig = tts[j];
+        float dn = key_t(key[j]);
+        uint32_t real_offset = 1;
+        for (uint32_t off = 1; j + off < n && (real_offset < 3 || key_face(key[j + off]) == TN_EMPTY ||
+                                               fabsf(__fsub_rn(key_t(key[j + off]), dn)) < TN_EPS); ++off) {
+            if (key_face(key[j + off]) == TN_EMPTY) continue;
+            uint32_t cell;
+            if (common_tet(orig, tts[j + off], cell)) {
+                const bool out = fabsf(__fsub_rn(key_t(key[j]), key_t(key[j + off]))) >= TN_EPS;
+                if (off > 1) {
+                    const u64 tk = key[j + off]; key[j + off] = key[j + 1]; key[j + 1] = tk;
+                    const uint2 tc = tts[j + off]; tts[j + off] = tts[j + 1]; tts[j + 1] = tc;
+                }
+                if (out) emit[jc++] = (uint16_t)j;
+                break;
+            }
+            dn = key_t(key[j + off]);
+            real_offset++;
+        }
+    }
+    return jc;
+}
+
+template <int MODE>  // 0: trace_rays (tetrahedra), 1: trace_rays_triangles (sorted raw face hits)
+__global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_count[TN_MAX_LEVELS], s_offset[TN_MAX_LEVELS];
+    if (threadIdx.x < TN_MAX_LEVELS) { s_count[threadIdx.x] = p.lv.count[threadIdx.x]; s_offset[threadIdx.x] = p.lv.offset[threadIdx.x]; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = (size_t)p.hcap * 8 + (size_t)p.scap * 4 + (size_t)p.lcap * 4;
+    unsigned char *base = smem_raw + (size_t)warp * per_warp;
+    u64 *hits = reinterpret_cast<u64 *>(base);
+    uint32_t *stack = reinterpret_cast<uint32_t *>(base + (size_t)p.hcap * 8);
+    uint32_t *leafq = stack + p.scap;
+    const uint32_t M = p.M;
+
+    for (uint32_t ray = blockIdx.x * TRACE_WARPS + warp; ray < p.R; ray += gridDim.x * TRACE_WARPS) {
+        const float ox = p.o[3 * (size_t)ray], oy = p.o[3 * (size_t)ray + 1], oz = p.o[3 * (size_t)ray + 2];
+        const float dx = p.d[3 * (size_t)ray], dy = p.d[3 * (size_t)ray + 1], dz = p.d[3 * (size_t)ray + 2];
+        const RaySetup rs = ray_setup(ox, oy, oz, dx, dy, dz);
+        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+        const float pad = 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + p.absmax);
+
+        uint32_t sc = 0, lc = 0, nh = 0;
+        u64 cutoff = ~0ull;
+        bool overflow = false;
+        if (rs.valid) {
+            if (lane == 0) stack[0] = (uint32_t)(p.lv.nlevels - 1) << 28;
+            sc = 1;
+        }
+        __syncwarp();
+
+        // ---------------- 1. all-hits gather ----------------
+        while (sc | lc) {
+            if (lc >= 32 || sc == 0) {
+                const uint32_t room = (p.hcap - nh) >> 2;
+                const uint32_t n = min(min(lc, 32u), room);
+                if (n == 0) {  // hit buffer full: nh > M-1 for sure, drop everything beyond the M-1 nearest
+                    cutoff = rank_select(hits, nh, M - 1, lane);
+                    continue;
+                }
+                u64 k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+                uint32_t fl = 0;
+                if (lane < n) {
+                    const uint32_t pos = leafq[lc - 1 - lane];
+                    const float4 *lp = reinterpret_cast<const float4 *>(p.leaves + pos);
+                    const float4 v0 = __ldg(lp), v1 = __ldg(lp + 1), v2 = __ldg(lp + 2), v3 = __ldg(lp + 3);
+                    const Sheared s0 = shear(rs, v0.x, v0.y, v0.z), s1 = shear(rs, v1.x, v1.y, v1.z);
+                    const Sheared s2 = shear(rs, v2.x, v2.y, v2.z), s3 = shear(rs, v3.x, v3.y, v3.z);
+                    const uint32_t f0 = __float_as_uint(v0.w), f1 = __float_as_uint(v1.w), f2 = __float_as_uint(v2.w), f3 = __float_as_uint(v3.w);
+                    float t, u, v;
+                    // face j = (v[(j+1)&3], v[(j+2)&3], v[(j+3)&3])   (src/tetrahedra_tracer.cpp:54-57)
+                    if ((f0 >> 31) && tri_test(s1, s2, s3, t, u, v)) { k0 = ((u64)__float_as_uint(t) << 32) | (f0 & 0x7FFFFFFFu); if (k0 < cutoff) fl |= 1u; }
+                    if ((f1 >> 31) && tri_test(s2, s3, s0, t, u, v)) { k1 = ((u64)__float_as_uint(t) << 32) | (f1 & 0x7FFFFFFFu); if (k1 < cutoff) fl |= 2u; }
+                    if ((f2 >> 31) && tri_test(s3, s0, s1, t, u, v)) { k2 = ((u64)__float_as_uint(t) << 32) | (f2 & 0x7FFFFFFFu); if (k2 < cutoff) fl |= 4u; }
+                    if ((f3 >> 31) && tri_test(s0, s1, s2, t, u, v)) { k3 = ((u64)__float_as_uint(t) << 32) | (f3 & 0x7FFFFFFFu); if (k3 < cutoff) fl |= 8u; }
+                }
+                const uint32_t c = __popc(fl);
+                const uint32_t incl = warp_incl_scan(c, lane);
+                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                uint32_t w = nh + incl - c;
+                if (fl & 1u) hits[w++] = k0;
+                if (fl & 2u) hits[w++] = k1;
+                if (fl & 4u) hits[w++] = k2;
+                if (fl & 8u) hits[w++] = k3;
+                nh += total;
+                lc -= n;
+                __syncwarp();
+            } else {
+                const uint32_t n = min(min(sc, 32u), (p.scap - sc) / 3u);
+                if (n == 0) { overflow = true; break; }
+                uint32_t hm = 0, cl = 1, cbase = 0;
+                if (lane < n) {
+                    const uint32_t e = stack[sc - 1 - lane];
+                    cl = (e >> 28) - 1u;
+                    cbase = (e & 0x0FFFFFFFu) << 2;
+                    const uint32_t nc = min(4u, s_count[cl] - cbase);
+                    const float4 *np = p.nodes + 2 * (size_t)(s_offset[cl] + cbase);
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; ++c) {
+                        if (c < nc) {
+                            const float4 a = __ldg(np + 2 * c), b = __ldg(np + 2 * c + 1);
+                            if (slab(a, b, ox, oy, oz, ix, iy, iz, pad)) hm |= 1u << c;
+                        }
+                    }
+                }
+                __syncwarp();  // all pops are done before anything is pushed over them
+                const uint32_t k = __popc(hm);
+                const uint32_t packed = (cl == 0) ? (k << 16) : k;
+                const uint32_t incl = warp_incl_scan(packed, lane);
+                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                const uint32_t excl = incl - packed;
+                uint32_t sb = sc - n + (excl & 0xFFFFu), lb = lc + (excl >> 16);
+#pragma unroll
+                for (uint32_t c = 0; c < 4; ++c) {
+                    if (hm & (1u << c)) {
+                        if (cl == 0) leafq[lb++] = cbase + c;
+                        else stack[sb++] = (cl << 28) | ((cbase + c) >> 0);
+                    }
+                }
+                sc = sc - n + (total & 0xFFFFu);
+                lc += total >> 16;
+                __syncwarp();
+            }
+        }
+        if (overflow) {
+            if (lane == 0) atomicAdd(p.flags, 1);
+            nh = 0;
+        }
+        if (nh > M - 1) rank_select(hits, nh, M - 1, lane);
+
+        // ---------------- 2. sort by (t, face id) ----------------
+        if (nh > 1) bitonic_sort_keys(hits, nh, lane);
+        __syncwarp();
+
+        const size_t row = (size_t)ray * M;
+        uint32_t jc = 0;
+        if (MODE == 1) {
+            // optix_trace_rays_triangles.cu:70-84 : sorted hits + their vertex ids
+            for (uint32_t j = lane; j < nh; j += 32) {
+                const uint32_t f = key_face(hits[j]);
+                const uint4 tr = __ldg(p.tri + f);
+                float t, u, v;
+                face_hit(rs, p.xyz, tr, t, u, v);
+                p.cells[row + j] = f;
+                p.dist[row + j] = t;
+                reinterpret_cast<float2 *>(p.bary)[row + j] = make_float2(u, v);
+                p.verts[3 * (row + j)] = tr.x; p.verts[3 * (row + j) + 1] = tr.y; p.verts[3 * (row + j) + 2] = tr.z;
+            }
+            jc = nh;
+            if (p.dense) {
+                for (uint32_t j = nh + lane; j < M; j += 32) {
+                    p.cells[row + j] = 0; p.dist[row + j] = 0.f;
+                    reinterpret_cast<float2 *>(p.bary)[row + j] = make_float2(0.f, 0.f);
+                    p.verts[3 * (row + j)] = 0; p.verts[3 * (row + j) + 1] = 0; p.verts[3 * (row + j) + 2] = 0;
+                }
+            }
+        } else {
+            // ---------------- 3. face pairing ----------------
+            uint2 *tts = reinterpret_cast<uint2 *>(stack);
+            uint16_t *emit = reinterpret_cast<uint16_t *>(leafq);
+            bool generic = true;
+            if (nh >= 2) {
+                for (uint32_t j = lane; j < nh; j += 32) tts[j] = __ldg(p.tt + key_face(hits[j]));
+                __syncwarp();
+                bool ok = true;
+                for (uint32_t j = lane; j + 1 < nh; j += 32) {
+                    uint32_t cell;
+                    if (fabsf(__fsub_rn(key_t(hits[j + 1]), key_t(hits[j]))) < TN_EPS) ok = false;
+                    if (!common_tet(tts[j], tts[j + 1], cell)) ok = false;
+                }
+                generic = __all_sync(FULL, ok);
+                if (generic) jc = nh - 1;
+                else {
+                    if (lane == 0) jc = post_process_serial(hits, tts, nh, emit);
+                    jc = __shfl_sync(FULL, jc, 0);
+                }
+                __syncwarp();
+            }
+            for (uint32_t r = lane; r < jc; r += 32) {
+                const uint32_t j = generic ? r : (uint32_t)emit[r];
+                const uint32_t f0 = key_face(hits[j]), f1 = key_face(hits[j + 1]);
+                const uint4 tr0 = __ldg(p.tri + f0), tr1 = __ldg(p.tri + f1);
+                float t0, u0, v0, t1, u1, v1;
+                face_hit(rs, p.xyz, tr0, t0, u0, v0);
+                face_hit(rs, p.xyz, tr1, t1, u1, v1);
+                uint32_t cell = TN_EMPTY;
+                common_tet(tts[j], tts[j + 1], cell);
+                // combine_indices (optix_trace_rays.cu:39-75)
+                const float b00 = __fsub_rn(__fsub_rn(1.0f, u0), v0);
+                const float r2[3] = {__fsub_rn(__fsub_rn(1.0f, u1), v1), u1, v1};
+                const uint32_t id1[3] = {tr0.x, tr0.y, tr0.z}, id2[3] = {tr1.x, tr1.y, tr1.z};
+                float o2[3] = {0.f, 0.f, 0.f};
+                uint32_t newv = 0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    bool was = false;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        if (!was && id1[q] == id2[i]) { o2[q] = r2[i]; was = true; }
+                    }
+                    if (!was) newv = id2[i];
+                }
+                const size_t g = row + r;
+                p.cells[g] = cell;
+                reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(newv, tr0.x, tr0.y, tr0.z);
+                float2 *bp = reinterpret_cast<float2 *>(p.bary + 6 * g);
+                bp[0] = make_float2(b00, u0);
+                bp[1] = make_float2(v0, o2[0]);
+                bp[2] = make_float2(o2[1], o2[2]);
+                reinterpret_cast<float2 *>(p.dist)[g] = make_float2(t0, t1);
+            }
+            if (p.dense) {
+                // phase 3 (optix_trace_rays.cu:260-265) + zeroed scratch tails (pinned, see oracle header)
+                for (uint32_t j = jc + lane; j < M; j += 32) {
+                    const size_t g = row + j;
+                    p.cells[g] = TN_EMPTY;
+                    reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(TN_EMPTY, TN_EMPTY, TN_EMPTY, TN_EMPTY);
+                    float2 *bp = reinterpret_cast<float2 *>(p.bary + 6 * g);
+                    bp[0] = make_float2(0.f, 0.f); bp[1] = make_float2(0.f, 0.f); bp[2] = make_float2(0.f, 0.f);
+                    reinterpret_cast<float2 *>(p.dist)[g] = make_float2(0.f, 0.f);
+                }
+            }
+        }
+        if (lane == 0) p.num[ray] = jc;
+        __syncwarp();
+    }
+}
+
+static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells,
+                        float *bary, float *dist, uint32_t *verts, int dense, cudaStream_t s) {
+    if (!h) return fail(TN_ERR_ARG, "null tracer");
+    if (M == 0 || (M & (M - 1)) != 0) return fail(TN_ERR_ARG, "max_ray_triangles must be a power of 2.");  // py_binding.cpp:44-47
+    if (M < 2 || M > 2048) return fail(TN_ERR_ARG, "max_ray_triangles must be in [2, 2048]");
+    if (!h->mesh.nodes) return fail(TN_ERR_STATE, "trace_rays: no tetrahedra loaded (call load_tetrahedra first)");
+    if (R == 0) return TN_OK;
+    DeviceGuard g(h->device);
+    TraceParams p;
+    p.o = o; p.d = d; p.R = R; p.M = M; p.num = num; p.cells = cells; p.bary = bary; p.dist = dist; p.verts = verts;
+    p.nodes = h->mesh.nodes; p.leaves = h->mesh.leaves; p.tri = (const uint4 *)h->mesh.tri; p.tt = (const uint2 *)h->mesh.tt;
+    p.xyz = h->mesh.xyz; p.lv = h->mesh.lv; p.absmax = h->mesh.absmax; p.dense = dense; p.flags = h->d_flags;
+    p.hcap = M + 128;
+    p.scap = M > 512 ? 2 * M : 1024;
+    p.lcap = M > 512 ? M / 2 : 256;
+    const size_t smem = (size_t)TRACE_WARPS * ((size_t)p.hcap * 8 + (size_t)p.scap * 4 + (size_t)p.lcap * 4);
+    auto kern = mode == 0 ? k_trace<0> : k_trace<1>;
+    TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 148, occ = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    TN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TRACE_WARPS * 32, smem));
+    if (occ < 1) occ = 1;
+    const uint32_t want = (R + TRACE_WARPS - 1) / TRACE_WARPS;
+    const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sms * occ));
+    kern<<<grid, TRACE_WARPS * 32, smem, s>>>(p);
+    h->launches += 1;
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+
+}  // namespace tn
+
+extern "C" int tn_trace_rays(tn_tracer *h, const float *d_origins, const float *d_directions, uint32_t R, uint32_t M, uint32_t *d_num,
+                             uint32_t *d_cells, float *d_bary, float *d_dist, uint32_t *d_verts, int dense, void *stream) {
+    return tn::launch_trace(h, 0, d_origins, d_directions, R, M, d_num, d_cells, d_bary, d_dist, d_verts, dense, (cudaStream_t)stream);
+}
+
+extern "C" int tn_trace_rays_triangles(tn_tracer *h, const float *d_origins, const float *d_directions, uint32_t R, uint32_t M,
+                                       uint32_t *d_num, uint32_t *d_faces, float *d_bary, float *d_dist, uint32_t *d_verts, void *stream) {
+    return tn::launch_trace(h, 1, d_origins, d_directions, R, M, d_num, d_faces, d_bary, d_dist, d_verts, 1, (cudaStream_t)stream);
+}
