@@ -1,0 +1,101 @@
+// tn_mlp_debug.cu -- one-tile bf16x3 GEMM on tcgen05 used by tests to validate, in isolation, the pieces
+// the fused MLP kernel relies on: weight image (hi/lo bf16, 128-byte swizzle) staged by TMA bulk copy,
+// A operand written into TMEM by tcgen05.st (thread = row), tcgen05.mma kind::f16 with A from TMEM,
+// accumulator read back with tcgen05.ld.  out[128,128] = A[128,K] * W[128,K]^T with ~fp32 accuracy.
+#include "tn_common.cuh"
+#include "tn_mlp_pack.cuh"
+#include "tn_tc.cuh"
+
+namespace tn {
+using namespace tc;
+
+__global__ void __launch_bounds__(160, 1) k_debug_gemm(const float *__restrict__ A, const uint8_t *__restrict__ wimg, uint32_t K,
+                                                        float *__restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *w_s = smem;  // K/64 * 32 KB
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 65536);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + 65536 + 64);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t wbytes = (K / 64) * 32768u;
+    if (warp == 4) {
+        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 512);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *tmem_ptr;
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars[0], wbytes);
+            for (uint32_t off = 0; off < wbytes; off += 16384) tma_bulk_g2s(w_s + off, wimg + off, 16384, &bars[0]);
+        }
+    } else {
+        const uint32_t row = threadIdx.x;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (uint32_t c = 0; c < K / 16; ++c) {  // 16 elements -> 8 packed columns
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_pack2(A[row * K + c * 16 + 2 * i], A[row * K + c * 16 + 2 * i + 1], hi[i], lo[i]);
+            tmem_st8(tbase + lane_base + 128 + c * 8, hi);
+            tmem_st8(tbase + lane_base + 192 + c * 8, lo);
+        }
+        tmem_st_wait();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (warp == 4 && lane == 0) {
+        mbar_wait(&bars[0], 0);
+        const uint32_t idesc = make_idesc_bf16(128, 128);
+        uint32_t acc = 0;
+        for (uint32_t kb = 0; kb < K / 64; ++kb) {
+            const uint32_t w_hi = smem_u32(w_s + kb * 32768u), w_lo = w_hi + 16384u;
+            for (int term = 0; term < 3; ++term) {  // (A_hi,W_hi) (A_lo,W_hi) (A_hi,W_lo)
+                const uint32_t a_col = (term == 1 ? 192u : 128u) + kb * 32u;
+                const uint32_t wb = term == 2 ? w_lo : w_hi;
+                for (uint32_t k = 0; k < 4; ++k) {
+                    mma_ts(tbase, tbase + a_col + k * 8, make_desc_sw128(wb + k * 32u), idesc, acc);
+                    acc = 1;
+                }
+            }
+        }
+        mma_commit(&bars[1]);
+    }
+    if (warp < 4) {
+        mbar_wait(&bars[1], 0);
+        fence_after_sync();
+        const uint32_t row = threadIdx.x;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (uint32_t ch = 0; ch < 4; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(tbase + lane_base + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) out[row * 128 + ch * 32 + i] = __uint_as_float(r[i]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace tn
+
+// test hook (not part of the reference surface): d_A f32[128,K], d_W f32[128,K] (nn.Linear layout), K in {64,128}
+extern "C" int tn_debug_gemm_bf16x3(int device, const float *d_A, const float *d_W, uint32_t K, float *d_out, void *stream) {
+    if (K != 64 && K != 128) return tn::fail(TN_ERR_ARG, "tn_debug_gemm_bf16x3: K must be 64 or 128");
+    tn::DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t *img = nullptr;
+    TN_CUDA(cudaMalloc(&img, (K / 64) * 32768));
+    tn::launch_pack_weights(d_W, K, 0, K, img, s);
+    const int smem = 65536 + 128;
+    TN_CUDA(cudaFuncSetAttribute(tn::k_debug_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tn::k_debug_gemm<<<1, 160, smem, s>>>(d_A, img, K, d_out);
+    TN_CUDA(cudaGetLastError());
+    TN_CUDA(cudaStreamSynchronize(s));
+    cudaFree(img);
+    return TN_OK;
+}

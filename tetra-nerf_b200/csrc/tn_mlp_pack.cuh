@@ -1,0 +1,30 @@
+// tn_mlp_pack.cuh -- weight image for the tensor-core MLP.
+// A Linear weight W[N=128][row_stride] (torch nn.Linear layout, in-features contiguous) restricted to
+// columns [k0, k0+K) is split into bf16 hi/lo and stored as the exact shared-memory image the UMMA
+// descriptor expects: for each 64-wide K block kb: [hi block 16 KB][lo block 16 KB], each block being
+// 128 rows x 128 bytes with the 128-byte swizzle (tc::sw128_offset).  K must be a multiple of 64.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "tn_tc.cuh"
+
+namespace tn {
+
+__global__ void k_pack_weights(const float *__restrict__ W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *__restrict__ img) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 128u * K) return;
+    const uint32_t n = idx / K, k = idx % K;
+    const float w = W[(size_t)n * row_stride + k0 + k];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    const uint32_t kb = k >> 6, kk = k & 63u;
+    const uint32_t off = kb * 32768u + tc::sw128_offset(n, kk);
+    *reinterpret_cast<__nv_bfloat16 *>(img + off) = hi;
+    *reinterpret_cast<__nv_bfloat16 *>(img + off + 16384u) = lo;
+}
+
+inline void launch_pack_weights(const float *W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *img, cudaStream_t s) {
+    k_pack_weights<<<(128u * K + 255u) / 256u, 256, 0, s>>>(W, row_stride, k0, K, img);
+}
+
+}  // namespace tn
