@@ -104,6 +104,14 @@ int tn_render_set_weights(tn_tracer *h, const float *const *d_params12, void *st
 /* d_rgb f32[R,3], d_acc f32[R,1], d_depth f32[R,1], d_mask u8[R] */
 int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
               float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, void *stream);
+/* ---- test hooks (not part of the reference surface) ------------------------------------------------
+ * device pointers of the intermediate buffers of the last tn_render call, in the order
+ * num, dist, n_active, ray_list, ebins_c, sbins_c, vi_c, bary_c, dens_c, ebins_f, vi_f, bary_f, out_f,
+ * dirbias, field shadow, weight image */
+int tn_render_debug_buffers(tn_tracer *h, void **ptrs16);
+/* one 128x128 tile out = A[128,K] * W[128,K]^T through the tcgen05 bf16x3 path; K in {64,128}; synchronous */
+int tn_debug_gemm_bf16x3(int device, const float *d_A, const float *d_W, uint32_t K, float *d_out, void *stream);
+
 /* number of kernels launched by this library on this tracer since creation (bench "gpu_launches") */
 uint64_t tn_launch_count(tn_tracer *h);
 

@@ -10,7 +10,7 @@
 
 namespace tn {
 
-__global__ void k_pack_weights(const float *__restrict__ W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *__restrict__ img) {
+static __global__ void k_pack_weights(const float *__restrict__ W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *__restrict__ img) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 128u * K) return;
     const uint32_t n = idx / K, k = idx % K;
@@ -23,7 +23,7 @@ __global__ void k_pack_weights(const float *__restrict__ W, uint32_t row_stride,
     *reinterpret_cast<__nv_bfloat16 *>(img + off + 16384u) = lo;
 }
 
-inline void launch_pack_weights(const float *W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *img, cudaStream_t s) {
+static inline void launch_pack_weights(const float *W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *img, cudaStream_t s) {
     k_pack_weights<<<(128u * K + 255u) / 256u, 256, 0, s>>>(W, row_stride, k0, K, img);
 }
 

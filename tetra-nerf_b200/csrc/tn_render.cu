@@ -1,11 +1,543 @@
-// tn_render.cu -- fused forward render (placeholder until the fused kernels land in this round).
+// tn_render.cu -- fused forward render: trace -> sample -> (interp+MLP on tcgen05) -> PDF -> (interp+MLP) -> composite.
+//
+// Replaces TetrahedraNerf.get_outputs between trace_rays and the pixel (tetranerf/nerfstudio/model.py:531-662)
+// in eval mode, i.e. the un-vendored nerfstudio pieces it calls (restated in oracle/oracle.py):
+//   k_sample_coarse : nears/fars + ray_mask (:531-545), TetrahedraSampler / UniformSampler bins (:111-122,141-192),
+//                     sample mid-points (:557) and find_visited_cells (tetrahedra_tracer.cu:115-161)
+//   k_mlp<false>    : interpolate_values + mlp_base + density head (:569-581)            [tn_mlp.cuh]
+//   k_sample_fine   : RaySamples.get_weights (:582), PDFSampler incl. include_original merge (:584),
+//                     mid-points, find_visited_cells (:585-594), direction encoding folded into a per-ray bias (:607)
+//   k_mlp<true>     : interpolate_values + mlp_base + density + mlp_head + colour head (:596-621)
+//   k_composite     : get_weights, RGB / accumulation / median-depth renderers, scatter to rays (:632-662)
+// Per-ray kernels use one warp per ray with the ray's segments staged in shared memory.
+#include <cmath>
+#include <vector>
+
 #include "tn_common.cuh"
+#include "tn_mlp.cuh"
+#include "tn_mlp_pack.cuh"
+
 namespace tn {
-struct RenderState { int dummy; };
-void free_render(tn_tracer *h) { delete h->render; h->render = nullptr; }
+
+int launch_trace_internal(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
+                          float *dist, uint32_t *verts, int dense, cudaStream_t s);
+
+struct RenderState {
+    // field
+    float *fshadow = nullptr;  // [V,64]
+    uint32_t V = 0;
+    // weights
+    uint8_t *wimg = nullptr;   // L1 32K | L2 64K | L3 64K | L4(base part) 64K
+    float *bias = nullptr;     // b1 b2 b3 [3][128]
+    float *head = nullptr;     // wd[128] wc[3][128] bd bc[3]
+    float *w4dir = nullptr;    // [128][27] + b4[128]
+    bool have_weights = false;
+    // workspace
+    size_t cap_R = 0, cap_M = 0, cap_Sc = 0, cap_S2 = 0;
+    uint32_t *num = nullptr, *cells = nullptr, *verts = nullptr;
+    float *bary = nullptr, *dist = nullptr;
+    uint32_t *n_active = nullptr, *ray_list = nullptr;
+    float *ebins_c = nullptr, *sbins_c = nullptr, *bary_c = nullptr, *dens_c = nullptr;
+    uint4 *vi_c = nullptr;
+    float *ebins_f = nullptr, *bary_f = nullptr, *out_f = nullptr, *dirbias = nullptr;
+    uint4 *vi_f = nullptr;
+};
+
+static void free_ws(RenderState *r) {
+    cudaFree(r->num); cudaFree(r->cells); cudaFree(r->verts); cudaFree(r->bary); cudaFree(r->dist);
+    cudaFree(r->n_active); cudaFree(r->ray_list); cudaFree(r->ebins_c); cudaFree(r->sbins_c); cudaFree(r->bary_c); cudaFree(r->dens_c);
+    cudaFree(r->vi_c); cudaFree(r->ebins_f); cudaFree(r->bary_f); cudaFree(r->out_f); cudaFree(r->dirbias); cudaFree(r->vi_f);
+    r->num = r->cells = r->verts = nullptr; r->bary = r->dist = nullptr; r->n_active = r->ray_list = nullptr;
+    r->ebins_c = r->sbins_c = r->bary_c = r->dens_c = nullptr; r->vi_c = nullptr;
+    r->ebins_f = r->bary_f = r->out_f = r->dirbias = nullptr; r->vi_f = nullptr;
+    r->cap_R = r->cap_M = r->cap_Sc = r->cap_S2 = 0;
+}
+
+void free_render(tn_tracer *h) {
+    if (!h->render) return;
+    RenderState *r = h->render;
+    free_ws(r);
+    cudaFree(r->fshadow); cudaFree(r->wimg); cudaFree(r->bias); cudaFree(r->head); cudaFree(r->w4dir);
+    delete r;
+    h->render = nullptr;
+}
+
+static RenderState *state(tn_tracer *h) {
+    if (!h->render) h->render = new RenderState();
+    return h->render;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_transpose64(const float *__restrict__ in, float *__restrict__ out, uint32_t V) {  // [64,V] -> [V,64]
+    __shared__ float tile[64][33];
+    const uint32_t v0 = blockIdx.x * 32;
+    for (uint32_t c = threadIdx.y; c < 64; c += blockDim.y) {
+        const uint32_t v = v0 + threadIdx.x;
+        tile[c][threadIdx.x] = v < V ? in[(size_t)c * V + v] : 0.f;
+    }
+    __syncthreads();
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t v = v0 + r;
+        if (v < V) {
+            out[(size_t)v * 64 + threadIdx.x] = tile[threadIdx.x][r];
+            out[(size_t)v * 64 + 32 + threadIdx.x] = tile[32 + threadIdx.x][r];
+        }
+    }
+}
+
+// head/bias packing: params12 order = mlp_base.layers.{0,1,2}.{weight,bias}, mlp_head.layers.0.{weight,bias},
+// field_output_color.net.{weight,bias}, field_output_density.net.{weight,bias}
+__global__ void k_pack_small(const float *b1, const float *b2, const float *b3, const float *w4, const float *b4, const float *wc,
+                             const float *bc, const float *wd, const float *bd, float *bias, float *head, float *w4dir) {
+    const int t = threadIdx.x;  // 128 threads
+    bias[t] = b1[t]; bias[128 + t] = b2[t]; bias[256 + t] = b3[t];
+    head[t] = wd[t];
+    head[128 + t] = wc[t]; head[256 + t] = wc[128 + t]; head[384 + t] = wc[256 + t];
+    if (t == 0) { head[512] = bd[0]; head[513] = bc[0]; head[514] = bc[1]; head[515] = bc[2]; }
+    for (int k = 0; k < 27; ++k) w4dir[t * 27 + k] = w4[t * 155 + k];  // mlp_out = [encoded_dir(27), base(128)] (model.py:608)
+    w4dir[128 * 27 + t] = b4[t];
+}
+
+// ---------------------------------------------------------------------------------------------------
+constexpr int SAMPLE_WARPS = 4;
+
+struct SampleParams {
+    uint32_t R, M, Sc, Sf, S2, biased;
+    const uint32_t *num;
+    const float2 *dist;
+    const uint4 *verts;
+    const float *bary;
+    const float *o, *d;
+    uint32_t *n_active, *ray_list;
+    float *ebins_c, *sbins_c, *bary_c;
+    uint4 *vi_c;
+    const float *dens_c;
+    float *ebins_f, *bary_f;
+    uint4 *vi_f;
+    float *dirbias;
+    const float *w4dir;
+    const float *out_f;
+    float *rgb, *acc, *depth;
+    uint8_t *mask;
+    float far_plane, bg0, bg1, bg2;
+};
+
+__device__ __forceinline__ float warp_incl_scan_f(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// in-place inclusive scan of a[0..n) in shared memory by one warp; returns the total
+__device__ float smem_scan_add(float *a, uint32_t n, int lane) {
+    float carry = 0.f;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        float v = i < n ? a[i] : 0.f;
+        v = warp_incl_scan_f(v, lane) + carry;
+        if (i < n) a[i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    __syncwarp();
+    return carry;
+}
+__device__ void smem_scan_max(const float *in, float *out, uint32_t n, int lane) {
+    float carry = -3.0e38f;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        float v = i < n ? in[i] : -3.0e38f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v = fmaxf(v, t);
+        }
+        v = fmaxf(v, carry);
+        if (i < n) out[i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ float nan_to_num_f(float x) {  // torch.nan_to_num defaults
+    if (isnan(x)) return 0.f;
+    if (isinf(x)) return x > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    return x;
+}
+// torch.linspace(start, end, steps)[i] for float32 (symmetric fill of ATen's linspace kernel)
+__device__ __forceinline__ float linspace_f(float start, float end, uint32_t steps, uint32_t i) {
+    const float step = (end - start) / (float)(steps - 1);
+    return i < steps / 2 ? start + step * (float)i : end - step * (float)(steps - i - 1);
+}
+
+// find_visited_cells for one sample distance d against staged segments (t_in, t_out, prefix-max of t_out)
+__device__ __forceinline__ void match_sample(float d, uint32_t n, const float *t_in, const float *t_out, const float *pm, size_t row,
+                                             const uint4 *__restrict__ verts, const float *__restrict__ bary, uint4 &vi, float &b0,
+                                             float &b1, float &b2) {
+    vi = make_uint4(TN_EMPTY, TN_EMPTY, TN_EMPTY, TN_EMPTY);
+    b0 = b1 = b2 = 0.f;
+    uint32_t lo = 0, hi = n;  // first p with pm[p] >= d  (== the reference's monotone pointer walk for sorted samples)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pm[mid] < d) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && t_in[lo] <= d) {
+        vi = __ldg(verts + row + lo);
+        const float mult = __fdiv_rn(__fsub_rn(d, t_in[lo]), __fsub_rn(t_out[lo], t_in[lo]));
+        const float omm = __fsub_rn(1.0f, mult);
+        const float *c = bary + 6 * (row + lo);
+        b0 = __fadd_rn(__fmul_rn(omm, __ldg(c)), __fmul_rn(mult, __ldg(c + 3)));
+        b1 = __fadd_rn(__fmul_rn(omm, __ldg(c + 1)), __fmul_rn(mult, __ldg(c + 4)));
+        b2 = __fadd_rn(__fmul_rn(omm, __ldg(c + 2)), __fmul_rn(mult, __ldg(c + 5)));
+    }
+}
+
+// shared memory per warp: 7 arrays (t_in t_out pm aux e x y) of A = max(M, Smax) + 2 floats each
+__host__ __device__ __forceinline__ size_t sample_arr(uint32_t M, uint32_t Smax) { return (size_t)(M > Smax ? M : Smax) + 2; }
+
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const SampleParams p) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ray = blockIdx.x * SAMPLE_WARPS + warp;
+    if (ray >= p.R) return;
+    const uint32_t M = p.M, S = p.Sc;
+    const size_t A = sample_arr(M, max(p.Sc, p.S2));
+    float *t_in = sm + (size_t)warp * 7 * A;
+    float *t_out = t_in + A, *pm = t_out + A, *cum = pm + A, *e = cum + A;
+    const uint32_t n = p.num[ray];
+    if (n == 0) {  // model.py:640-650 : background colour, accumulation 0, depth = collider far plane
+        if (lane == 0) {
+            p.rgb[3 * (size_t)ray] = p.bg0; p.rgb[3 * (size_t)ray + 1] = p.bg1; p.rgb[3 * (size_t)ray + 2] = p.bg2;
+            p.acc[ray] = 0.f; p.depth[ray] = p.far_plane; p.mask[ray] = 0;
+        }
+        return;
+    }
+    uint32_t slot = 0;
+    if (lane == 0) { slot = atomicAdd(p.n_active, 1u); p.ray_list[slot] = ray; p.mask[ray] = 1; }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    const size_t row = (size_t)ray * M;
+    for (uint32_t k = lane; k < n; k += 32) { const float2 h = p.dist[row + k]; t_in[k] = h.x; t_out[k] = h.y; }
+    __syncwarp();
+    const float near = t_in[0], far = t_out[n - 1];
+    smem_scan_max(t_out, pm, n, lane);
+    if (p.biased) {  // map_from_real_distances_to_biased_with_bounds, model.py:111-122
+        if (lane == 0) cum[0] = near;
+        for (uint32_t k = lane; k < n; k += 32) cum[k + 1] = fmaxf(t_out[k] - t_in[k], 0.f);
+        __syncwarp();
+        // cum[k] = start + sum_{i<k} len_i : scan over [start, len_0, len_1, ...]
+        smem_scan_add(cum, n + 1, lane);
+    }
+    for (uint32_t j = lane; j <= S; j += 32) {
+        const float b = linspace_f(0.f, 1.f, S + 1, j);
+        float eu = b * far + (1.f - b) * near;  // spacing_to_euclidean_fn (model.py:177)
+        float sb = b;
+        if (p.biased) {
+            const float uni = (eu - near) / (far - near);
+            float rest = uni * (float)n;
+            float iv = fminf(floorf(rest), (float)(n - 1));
+            iv = fmaxf(iv, 0.f);
+            rest = rest - iv;
+            const uint32_t k = (uint32_t)iv;
+            const float len = fmaxf(t_out[k] - t_in[k], 0.f);
+            eu = cum[k] + len * rest;
+            sb = (eu - near) / (far - near);  // model.py:182
+        }
+        e[j] = eu;
+        p.ebins_c[(size_t)slot * (S + 1) + j] = eu;
+        p.sbins_c[(size_t)slot * (S + 1) + j] = sb;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < S; j += 32) {
+        const float dmid = (e[j + 1] + e[j]) / 2.f;  // model.py:557
+        uint4 vi; float b0, b1, b2;
+        match_sample(dmid, n, t_in, t_out, pm, row, p.verts, p.bary, vi, b0, b1, b2);
+        const size_t g = (size_t)slot * S + j;
+        p.vi_c[g] = vi;
+        p.bary_c[3 * g] = b0; p.bary_c[3 * g + 1] = b1; p.bary_c[3 * g + 2] = b2;
+    }
+}
+
+// RaySamples.get_weights on staged deltas/densities: w[j] (in place over `dd`), using `tr` as scratch
+__device__ void weights_from_density(float *dd, float *tr, uint32_t S, int lane) {
+    for (uint32_t j = lane; j < S; j += 32) tr[j] = dd[j];
+    __syncwarp();
+    smem_scan_add(tr, S, lane);  // inclusive cumsum of delta*density
+    for (uint32_t j = lane; j < S; j += 32) {
+        const float excl = j == 0 ? 0.f : tr[j - 1];
+        const float alpha = 1.f - expf(-dd[j]);
+        const float T = expf(-excl);
+        dd[j] = nan_to_num_f(alpha * T);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_fine(const SampleParams p) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * SAMPLE_WARPS + warp;
+    if (slot >= *p.n_active) return;
+    const uint32_t M = p.M, S = p.Sc, S2 = p.S2, nb = p.Sf + 1;
+    const size_t A = sample_arr(M, max(p.Sc, p.S2));
+    float *t_in = sm + (size_t)warp * 7 * A;
+    float *t_out = t_in + A, *pm = t_out + A, *cdf = pm + A, *e = cdf + A, *x = e + A, *y = x + A;
+    const uint32_t ray = p.ray_list[slot];
+    const uint32_t n = p.num[ray];
+    const size_t row = (size_t)ray * M;
+    for (uint32_t k = lane; k < n; k += 32) { const float2 h = p.dist[row + k]; t_in[k] = h.x; t_out[k] = h.y; }
+    __syncwarp();
+    const float near = t_in[0], far = t_out[n - 1];
+    smem_scan_max(t_out, pm, n, lane);
+    // ---- coarse weights (model.py:581-582) ----
+    const float *eb = p.ebins_c + (size_t)slot * (S + 1);
+    const float *sbc = p.sbins_c + (size_t)slot * (S + 1);
+    for (uint32_t j = lane; j < S; j += 32) x[j] = (eb[j + 1] - eb[j]) * p.dens_c[(size_t)slot * S + j];
+    __syncwarp();
+    weights_from_density(x, y, S, lane);
+    // ---- PDFSampler (nerfstudio ray_samplers.py), histogram_padding 0.01, eps 1e-5, eval mode ----
+    float part = 0.f;
+    for (uint32_t j = lane; j < S; j += 32) { x[j] = x[j] + 0.01f; part += x[j]; }
+    float wsum = warp_sum_f(part);
+    const float padding = fmaxf(1e-5f - wsum, 0.f);
+    wsum += padding;
+    for (uint32_t j = lane; j < S; j += 32) y[j] = (x[j] + padding / (float)S) / wsum;  // pdf
+    __syncwarp();
+    smem_scan_add(y, S, lane);
+    if (lane == 0) cdf[0] = 0.f;
+    for (uint32_t j = lane; j < S; j += 32) cdf[j + 1] = fminf(1.f, y[j]);
+    __syncwarp();
+    // new bins -> x[0..nb)
+    const float u_end = (float)(1.0 - 1.0 / (double)nb), u_off = (float)(1.0 / (2.0 * (double)nb));
+    for (uint32_t i = lane; i < nb; i += 32) {
+        const float u = linspace_f(0.f, u_end, nb, i) + u_off;
+        uint32_t lo = 0, hi = S + 1;  // searchsorted(cdf, u, side="right"): first idx with cdf[idx] > u
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+        const uint32_t below = (uint32_t)min(max((int)lo - 1, 0), (int)S), above = min(lo, S);
+        const float c0 = cdf[below], c1 = cdf[above];
+        float t = (u - c0) / (c1 - c0);
+        t = isnan(t) ? 0.f : nan_to_num_f(t);
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        const float b0 = sbc[below], b1 = sbc[above];
+        x[i] = b0 + t * (b1 - b0);
+    }
+    __syncwarp();
+    // merge existing (S+1, sorted) with new (nb, sorted) -> e[0..S2]  (torch.sort of the concatenation)
+    for (uint32_t k = lane; k <= S; k += 32) {
+        const float v = sbc[k];
+        uint32_t lo = 0, hi = nb;  // # new strictly less than v
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (x[mid] < v) lo = mid + 1; else hi = mid; }
+        e[k + lo] = v;
+    }
+    for (uint32_t i = lane; i < nb; i += 32) {
+        const float v = x[i];
+        uint32_t lo = 0, hi = S + 1;  // # existing <= v
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sbc[mid] <= v) lo = mid + 1; else hi = mid; }
+        e[i + lo] = v;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j <= S2; j += 32) {
+        const float b = e[j];
+        const float eu = b * far + (1.f - b) * near;
+        y[j] = eu;
+        p.ebins_f[(size_t)slot * (S2 + 1) + j] = eu;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < S2; j += 32) {
+        const float dmid = (y[j + 1] + y[j]) / 2.f;  // model.py:585
+        uint4 vi; float b0, b1, b2;
+        match_sample(dmid, n, t_in, t_out, pm, row, p.verts, p.bary, vi, b0, b1, b2);
+        const size_t g = (size_t)slot * S2 + j;
+        p.vi_f[g] = vi;
+        p.bary_f[3 * g] = b0; p.bary_f[3 * g + 1] = b1; p.bary_f[3 * g + 2] = b2;
+    }
+    // ---- direction encoding folded into a per-ray bias of mlp_head (model.py:607-620) ----
+    // NeRFEncoding(in_dim=3, num_frequencies=4, min_freq_exp=0, max_freq_exp=4, include_input=True), model.py:426-432
+    const float dx = p.d[3 * (size_t)ray], dy = p.d[3 * (size_t)ray + 1], dz = p.d[3 * (size_t)ray + 2];
+    float enc[27];
+    {
+        const float dd[3] = {dx, dy, dz};
+        const float two_pi = 6.283185307179586f, half_pi = 1.5707963267948966f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float sc = two_pi * dd[a];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const float freq = f == 0 ? 1.0f : (f == 1 ? 2.5198421f : (f == 2 ? 6.3496042f : 16.0f));  // 2**linspace(0,4,4)
+                const float si = sc * freq;
+                enc[a * 4 + f] = sinf(si);
+                enc[12 + a * 4 + f] = sinf(si + half_pi);
+            }
+            enc[24 + a] = dd[a];
+        }
+    }
+    for (uint32_t o = lane; o < 128; o += 32) {
+        float acc = p.w4dir[128 * 27 + o];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) acc = fmaf(__ldg(p.w4dir + o * 27 + k), enc[k], acc);
+        p.dirbias[(size_t)slot * 128 + o] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_composite(const SampleParams p) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * SAMPLE_WARPS + warp;
+    if (slot >= *p.n_active) return;
+    const uint32_t S2 = p.S2;
+    float *w = sm + (size_t)warp * (2 * ((size_t)S2 + 2)), *tr = w + S2 + 2;
+    const uint32_t ray = p.ray_list[slot];
+    const float *eb = p.ebins_f + (size_t)slot * (S2 + 1);
+    const float4 *of = reinterpret_cast<const float4 *>(p.out_f) + (size_t)slot * S2;
+    for (uint32_t j = lane; j < S2; j += 32) w[j] = (eb[j + 1] - eb[j]) * of[j].x;
+    __syncwarp();
+    weights_from_density(w, tr, S2, lane);  // model.py:632
+    float r = 0.f, g = 0.f, b = 0.f, a = 0.f;
+    for (uint32_t j = lane; j < S2; j += 32) {
+        const float4 c = of[j];
+        const float wj = w[j];
+        r += wj * nan_to_num_f(c.y); g += wj * nan_to_num_f(c.z); b += wj * nan_to_num_f(c.w); a += wj;
+    }
+    r = warp_sum_f(r); g = warp_sum_f(g); b = warp_sum_f(b); a = warp_sum_f(a);
+    // DepthRenderer("median"): first sample whose cumulative weight reaches 0.5
+    for (uint32_t j = lane; j < S2; j += 32) tr[j] = w[j];
+    __syncwarp();
+    smem_scan_add(tr, S2, lane);
+    uint32_t first = S2;
+    for (uint32_t j = lane; j < S2; j += 32) if (tr[j] >= 0.5f) { first = j; break; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    const uint32_t mi = min(first, S2 - 1);
+    if (lane == 0) {
+        // RGBRenderer (eval): comp + background * (1 - acc), clamped to [0,1]
+        p.rgb[3 * (size_t)ray] = fminf(fmaxf(r + p.bg0 * (1.f - a), 0.f), 1.f);
+        p.rgb[3 * (size_t)ray + 1] = fminf(fmaxf(g + p.bg1 * (1.f - a), 0.f), 1.f);
+        p.rgb[3 * (size_t)ray + 2] = fminf(fmaxf(b + p.bg2 * (1.f - a), 0.f), 1.f);
+        p.acc[ray] = a;
+        p.depth[ray] = (eb[mi] + eb[mi + 1]) / 2.f;
+    }
+}
+
+// single-pass configuration (num_fine_samples == 0): colours come from the first and only pass; handled by
+// running the FINE MLP on the coarse samples (dirbias computed by k_dirbias_only).
+__global__ void k_dirbias_only(const SampleParams p) { /* reserved */ }
+
+static int ensure_ws(RenderState *r, size_t R, size_t M, size_t Sc, size_t S2) {
+    if (R <= r->cap_R && M <= r->cap_M && Sc <= r->cap_Sc && S2 <= r->cap_S2) return TN_OK;
+    free_ws(r);
+    R = std::max(R, r->cap_R); M = std::max(M, r->cap_M); Sc = std::max(Sc, r->cap_Sc); S2 = std::max(S2, r->cap_S2);
+#define A(ptr, bytes) TN_CUDA(cudaMalloc((void **)&(ptr), (bytes)))
+    A(r->num, 4 * R); A(r->cells, 4 * R * M); A(r->verts, 16 * R * M); A(r->bary, 24 * R * M); A(r->dist, 8 * R * M);
+    A(r->n_active, 16); A(r->ray_list, 4 * R);
+    A(r->ebins_c, 4 * R * (Sc + 1)); A(r->sbins_c, 4 * R * (Sc + 1)); A(r->bary_c, 12 * R * Sc); A(r->dens_c, 4 * R * Sc); A(r->vi_c, 16 * R * Sc);
+    A(r->ebins_f, 4 * R * (S2 + 1)); A(r->bary_f, 12 * R * S2); A(r->out_f, 16 * R * S2); A(r->dirbias, 512 * R); A(r->vi_f, 16 * R * S2);
+#undef A
+    r->cap_R = R; r->cap_M = M; r->cap_Sc = Sc; r->cap_S2 = S2;
+    return TN_OK;
+}
+
 }  // namespace tn
-extern "C" int tn_render_set_field(tn_tracer *, const float *, uint32_t, uint32_t, void *) { return tn::fail(TN_ERR_STATE, "tn_render: not built"); }
-extern "C" int tn_render_set_weights(tn_tracer *, const float *const *, void *) { return tn::fail(TN_ERR_STATE, "tn_render: not built"); }
-extern "C" int tn_render(tn_tracer *, const tn_render_config *, const float *, const float *, uint32_t, float *, float *, float *, uint8_t *, void *) {
-    return tn::fail(TN_ERR_STATE, "tn_render: not built");
+
+using namespace tn;
+
+extern "C" int tn_render_set_field(tn_tracer *h, const float *d_field, uint32_t C, uint32_t V, void *stream) {
+    if (!h) return fail(TN_ERR_ARG, "null tracer");
+    if (C != 64) return fail(TN_ERR_ARG, "tn_render: field_dim must be 64 (model.py:81)");
+    DeviceGuard g(h->device);
+    RenderState *r = state(h);
+    if (r->V != V) { cudaFree(r->fshadow); r->fshadow = nullptr; TN_CUDA(cudaMalloc((void **)&r->fshadow, sizeof(float) * 64 * (size_t)V)); r->V = V; }
+    k_transpose64<<<(V + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_field, r->fshadow, V);
+    h->launches += 1;
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+
+extern "C" int tn_render_set_weights(tn_tracer *h, const float *const *P, void *stream) {
+    if (!h || !P) return fail(TN_ERR_ARG, "null argument");
+    DeviceGuard g(h->device);
+    RenderState *r = state(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!r->wimg) {
+        TN_CUDA(cudaMalloc((void **)&r->wimg, 32768 + 3 * 65536));
+        TN_CUDA(cudaMalloc((void **)&r->bias, sizeof(float) * 384));
+        TN_CUDA(cudaMalloc((void **)&r->head, sizeof(float) * 520));
+        TN_CUDA(cudaMalloc((void **)&r->w4dir, sizeof(float) * (128 * 27 + 128)));
+    }
+    launch_pack_weights(P[0], 64, 0, 64, r->wimg, s);                     // mlp_base.layers.0.weight [128,64]
+    launch_pack_weights(P[2], 128, 0, 128, r->wimg + 32768, s);           // mlp_base.layers.1.weight [128,128]
+    launch_pack_weights(P[4], 128, 0, 128, r->wimg + 32768 + 65536, s);   // mlp_base.layers.2.weight
+    launch_pack_weights(P[6], 155, 27, 128, r->wimg + 32768 + 131072, s); // mlp_head.layers.0.weight [128,155], base part
+    k_pack_small<<<1, 128, 0, s>>>(P[1], P[3], P[5], P[6], P[7], P[8], P[9], P[10], P[11], r->bias, r->head, r->w4dir);
+    h->launches += 5;
+    TN_CUDA(cudaGetLastError());
+    r->have_weights = true;
+    return TN_OK;
+}
+
+extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
+                         float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, void *stream) {
+    if (!h || !cfg) return fail(TN_ERR_ARG, "null argument");
+    RenderState *r = h->render;
+    if (!r || !r->fshadow || !r->have_weights) return fail(TN_ERR_STATE, "tn_render: call tn_render_set_field and tn_render_set_weights first");
+    if (!h->mesh.nodes) return fail(TN_ERR_STATE, "tn_render: no tetrahedra loaded");
+    if (r->V != h->mesh.V) return fail(TN_ERR_ARG, "tn_render: field has a different vertex count than the mesh");
+    const uint32_t M = cfg->max_ray_triangles, Sc = cfg->num_samples, Sf = cfg->num_fine_samples;
+    if (Sc == 0 || Sc > 4096 || Sf > 4096) return fail(TN_ERR_ARG, "tn_render: num_samples must be in [1,4096]");
+    if (Sf == 0) return fail(TN_ERR_ARG, "tn_render: num_fine_samples == 0 is not supported by the fused path (use the unfused ops)");
+    if (R == 0) return TN_OK;
+    const uint32_t S2 = Sc + Sf + 1;  // PDFSampler include_original (model.py:463)
+    DeviceGuard g(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure_ws(r, R, M, Sc, S2);
+    if (rc) return rc;
+    rc = launch_trace_internal(h, d_origins, d_directions, R, M, r->num, r->cells, r->bary, r->dist, r->verts, 0, s);
+    if (rc) return rc;
+    TN_CUDA(cudaMemsetAsync(r->n_active, 0, 16, s));
+    SampleParams p{};
+    p.R = R; p.M = M; p.Sc = Sc; p.Sf = Sf; p.S2 = S2; p.biased = cfg->use_biased_sampler;
+    p.num = r->num; p.dist = (const float2 *)r->dist; p.verts = (const uint4 *)r->verts; p.bary = r->bary;
+    p.o = d_origins; p.d = d_directions; p.n_active = r->n_active; p.ray_list = r->ray_list;
+    p.ebins_c = r->ebins_c; p.sbins_c = r->sbins_c; p.bary_c = r->bary_c; p.vi_c = r->vi_c; p.dens_c = r->dens_c;
+    p.ebins_f = r->ebins_f; p.bary_f = r->bary_f; p.vi_f = r->vi_f; p.dirbias = r->dirbias; p.w4dir = r->w4dir; p.out_f = r->out_f;
+    p.rgb = d_rgb; p.acc = d_acc; p.depth = d_depth; p.mask = d_mask;
+    p.far_plane = cfg->far_plane; p.bg0 = cfg->background[0]; p.bg1 = cfg->background[1]; p.bg2 = cfg->background[2];
+    const uint32_t Smax = std::max(Sc, S2);
+    const size_t smem_s = SAMPLE_WARPS * sizeof(float) * 7 * sample_arr(M, Smax);
+    const size_t smem_c = SAMPLE_WARPS * sizeof(float) * 2 * ((size_t)S2 + 2);
+    TN_CUDA(cudaFuncSetAttribute(k_sample_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    TN_CUDA(cudaFuncSetAttribute(k_sample_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    TN_CUDA(cudaFuncSetAttribute(k_composite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    TN_CUDA(cudaFuncSetAttribute(k_mlp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    TN_CUDA(cudaFuncSetAttribute(k_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const uint32_t gridR = (R + SAMPLE_WARPS - 1) / SAMPLE_WARPS;
+
+    k_sample_coarse<<<gridR, SAMPLE_WARPS * 32, smem_s, s>>>(p);
+    MlpParams mc{};
+    mc.n_active = r->n_active; mc.S = Sc; mc.vi = r->vi_c; mc.bary = r->bary_c; mc.fshadow = r->fshadow; mc.wimg = r->wimg;
+    mc.bias = r->bias; mc.head = r->head; mc.dirbias = nullptr; mc.out = r->dens_c;
+    const uint32_t tiles_c = (uint32_t)(((uint64_t)R * Sc + 127) / 128), tiles_f = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
+    k_mlp<false><<<std::min<uint32_t>(tiles_c, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mc);
+    k_sample_fine<<<gridR, SAMPLE_WARPS * 32, smem_s, s>>>(p);
+    MlpParams mf = mc;
+    mf.S = S2; mf.vi = r->vi_f; mf.bary = r->bary_f; mf.dirbias = r->dirbias; mf.out = r->out_f;
+    k_mlp<true><<<std::min<uint32_t>(tiles_f, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mf);
+    k_composite<<<gridR, SAMPLE_WARPS * 32, smem_c, s>>>(p);
+    h->launches += 5;
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+
+// test / debug hook: device pointers of the intermediate buffers of the last tn_render call
+extern "C" int tn_render_debug_buffers(tn_tracer *h, void **ptrs16) {
+    if (!h || !h->render) return fail(TN_ERR_STATE, "no render state");
+    RenderState *r = h->render;
+    void *v[16] = {r->num, r->dist, r->n_active, r->ray_list, r->ebins_c, r->sbins_c, r->vi_c, r->bary_c,
+                   r->dens_c, r->ebins_f, r->vi_f, r->bary_f, r->out_f, r->dirbias, r->fshadow, r->wimg};
+    for (int i = 0; i < 16; ++i) ptrs16[i] = v[i];
+    return TN_OK;
 }

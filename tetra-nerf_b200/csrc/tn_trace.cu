@@ -397,6 +397,11 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
     return TN_OK;
 }
 
+int launch_trace_internal(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
+                          float *dist, uint32_t *verts, int dense, cudaStream_t s) {
+    return launch_trace(h, 0, o, d, R, M, num, cells, bary, dist, verts, dense, s);
+}
+
 }  // namespace tn
 
 extern "C" int tn_trace_rays(tn_tracer *h, const float *d_origins, const float *d_directions, uint32_t R, uint32_t M, uint32_t *d_num,
