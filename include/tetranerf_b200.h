@@ -104,6 +104,10 @@ int tn_render_set_weights(tn_tracer *h, const float *const *d_params12, void *st
 /* d_rgb f32[R,3], d_acc f32[R,1], d_depth f32[R,1], d_mask u8[R] */
 int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
               float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, void *stream);
+/* per-kernel CUDA-event timing of the last tn_render call: ms6 = trace, sample_coarse, mlp_coarse, sample_fine,
+ * mlp_fine, composite (used by bench.py for the roofline of the dominant kernel) */
+int tn_render_set_profiling(tn_tracer *h, int enable);
+int tn_render_get_timings(tn_tracer *h, float *ms6);
 /* ---- test hooks (not part of the reference surface) ------------------------------------------------
  * device pointers of the intermediate buffers of the last tn_render call, in the order
  * num, dist, n_active, ray_list, ebins_c, sbins_c, vi_c, bary_c, dens_c, ebins_f, vi_f, bary_f, out_f,

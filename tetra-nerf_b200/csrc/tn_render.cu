@@ -41,6 +41,9 @@ struct RenderState {
     uint4 *vi_c = nullptr;
     float *ebins_f = nullptr, *bary_f = nullptr, *out_f = nullptr, *dirbias = nullptr;
     uint4 *vi_f = nullptr;
+    // optional per-kernel timing (bench.py roofline): events around the 6 kernels of tn_render
+    bool profile = false;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static void free_ws(RenderState *r) {
@@ -58,6 +61,7 @@ void free_render(tn_tracer *h) {
     RenderState *r = h->render;
     free_ws(r);
     cudaFree(r->fshadow); cudaFree(r->wimg); cudaFree(r->bias); cudaFree(r->head); cudaFree(r->w4dir);
+    for (auto &e : r->ev) if (e) cudaEventDestroy(e);
     delete r;
     h->render = nullptr;
 }
@@ -493,9 +497,12 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     cudaStream_t s = (cudaStream_t)stream;
     int rc = ensure_ws(r, R, M, Sc, S2);
     if (rc) return rc;
+    TN_CUDA(cudaMemsetAsync(r->n_active, 0, 16, s));
+#define TN_EV(i) do { if (r->profile) cudaEventRecord(r->ev[i], s); } while (0)
+    TN_EV(0);
     rc = launch_trace_internal(h, d_origins, d_directions, R, M, r->num, r->cells, r->bary, r->dist, r->verts, 0, s);
     if (rc) return rc;
-    TN_CUDA(cudaMemsetAsync(r->n_active, 0, 16, s));
+    TN_EV(1);
     SampleParams p{};
     p.R = R; p.M = M; p.Sc = Sc; p.Sf = Sf; p.S2 = S2; p.biased = cfg->use_biased_sampler;
     p.num = r->num; p.dist = (const float2 *)r->dist; p.verts = (const uint4 *)r->verts; p.bary = r->bary;
@@ -517,18 +524,43 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     const uint32_t gridR = (R + SAMPLE_WARPS - 1) / SAMPLE_WARPS;
 
     k_sample_coarse<<<gridR, SAMPLE_WARPS * 32, smem_s, s>>>(p);
+    TN_EV(2);
     MlpParams mc{};
     mc.n_active = r->n_active; mc.S = Sc; mc.vi = r->vi_c; mc.bary = r->bary_c; mc.fshadow = r->fshadow; mc.wimg = r->wimg;
     mc.bias = r->bias; mc.head = r->head; mc.dirbias = nullptr; mc.out = r->dens_c;
     const uint32_t tiles_c = (uint32_t)(((uint64_t)R * Sc + 127) / 128), tiles_f = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
     k_mlp<false><<<std::min<uint32_t>(tiles_c, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mc);
+    TN_EV(3);
     k_sample_fine<<<gridR, SAMPLE_WARPS * 32, smem_s, s>>>(p);
+    TN_EV(4);
     MlpParams mf = mc;
     mf.S = S2; mf.vi = r->vi_f; mf.bary = r->bary_f; mf.dirbias = r->dirbias; mf.out = r->out_f;
     k_mlp<true><<<std::min<uint32_t>(tiles_f, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mf);
+    TN_EV(5);
     k_composite<<<gridR, SAMPLE_WARPS * 32, smem_c, s>>>(p);
+    TN_EV(6);
+#undef TN_EV
     h->launches += 5;
     TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+
+// per-kernel timing of the LAST tn_render call (trace, sample_coarse, mlp_coarse, sample_fine, mlp_fine, composite), ms.
+// enable with tn_render_set_profiling(h, 1); the getter synchronises on the last event.
+extern "C" int tn_render_set_profiling(tn_tracer *h, int enable) {
+    if (!h) return fail(TN_ERR_ARG, "null tracer");
+    DeviceGuard g(h->device);
+    RenderState *r = state(h);
+    if (enable) for (auto &e : r->ev) if (!e) TN_CUDA(cudaEventCreate(&e));
+    r->profile = enable != 0;
+    return TN_OK;
+}
+extern "C" int tn_render_get_timings(tn_tracer *h, float *ms6) {
+    if (!h || !h->render || !h->render->profile) return fail(TN_ERR_STATE, "profiling is not enabled");
+    DeviceGuard g(h->device);
+    RenderState *r = h->render;
+    TN_CUDA(cudaEventSynchronize(r->ev[6]));
+    for (int i = 0; i < 6; ++i) TN_CUDA(cudaEventElapsedTime(&ms6[i], r->ev[i], r->ev[i + 1]));
     return TN_OK;
 }
 

@@ -25,6 +25,9 @@ _lib.tn_render_set_field.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, _vp]
 _lib.tn_render_set_weights.argtypes = [_vp, C.POINTER(_vp), _vp]
 _lib.tn_render.argtypes = [_vp, C.POINTER(_Cfg), _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]
 _lib.tn_render_debug_buffers.argtypes = [_vp, C.POINTER(_vp)]
+_lib.tn_render_set_profiling.argtypes = [_vp, C.c_int]
+_lib.tn_render_get_timings.argtypes = [_vp, C.POINTER(C.c_float)]
+KERNEL_NAMES = ["trace", "sample_coarse", "mlp_coarse", "sample_fine", "mlp_fine", "composite"]
 
 PARAM_ORDER = [
     "mlp_base.layers.0.weight", "mlp_base.layers.0.bias", "mlp_base.layers.1.weight", "mlp_base.layers.1.bias",
@@ -99,6 +102,15 @@ class FusedRenderer:
         ext._check(_lib.tn_render(tr.handle, C.byref(cfg), origins.data_ptr(), directions.data_ptr(), R, out["rgb"].data_ptr(),
                                   out["accumulation"].data_ptr(), out["depth"].data_ptr(), out["ray_mask"].data_ptr(), self._stream()))
         return out
+
+    def set_profiling(self, enable: bool) -> None:
+        ext._check(_lib.tn_render_set_profiling(self.tracer.handle, int(enable)))
+
+    def kernel_timings_ms(self) -> Dict[str, float]:
+        """CUDA-event durations of the six kernels of the last render() (profiling must be enabled)."""
+        arr = (C.c_float * 6)()
+        ext._check(_lib.tn_render_get_timings(self.tracer.handle, arr))
+        return {n: float(arr[i]) for i, n in enumerate(KERNEL_NAMES)}
 
     def debug_buffers(self):
         arr = (_vp * 16)()
