@@ -99,3 +99,73 @@ extern "C" int tn_debug_gemm_bf16x3(int device, const float *d_A, const float *d
     cudaFree(img);
     return TN_OK;
 }
+
+// ---- microbenchmark: cycles per tcgen05.mma (M=128, N=128, K=16, bf16) in TS (A from TMEM) and SS (A from smem) mode ----
+namespace tn {
+using namespace tc;
+__global__ void __launch_bounds__(160, 1) k_debug_mma_rate(long long *out, int nrep, int mode, uint32_t boff) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 212992);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + 212992 + 64);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < 212992 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    if (warp == 4) {
+        if (lane == 0) { mbar_init(&bars[0], 1); fence_barrier_init(); }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 512);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *tmem_ptr;
+    if (warp < 4 && (mode & 4)) {
+        // concurrent epilogue-like TMEM traffic on the other accumulator: ld 32 cols + st 16 cols in a loop
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        uint32_t r[32];
+        for (int it = 0; it < nrep * 6; ++it) {
+            tmem_ld32(tbase + lane_base + 256u + (uint32_t)(it & 3) * 32u, r);
+            tmem_ld_wait();
+            tmem_st16(tbase + lane_base + 384u + (uint32_t)(it & 3) * 16u, r);
+            tmem_st_wait();
+        }
+    }
+    if (warp == 4 && lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, 128);
+        const uint64_t dw = make_desc_sw128(smem_u32(smem + boff));
+        const long long t0 = clock64();
+        for (int r = 0; r < nrep; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                // mode 0: TS, one accumulator; 1: TS, two accumulators alternating; 2: SS, one accumulator; 3: SS two accumulators
+                const uint32_t d = tbase + ((mode & 1) ? (uint32_t)(k & 1) * 256u : 0u);
+                const uint64_t b = dw + (uint64_t)((k & 3) * 2 + (k >> 2) * 1024);
+                if ((mode & 3) < 2) mma_ts_c<true>(d, tbase + 128u + (uint32_t)k * 8u, b, idesc);
+                else mma_ss(d, dw + 4096ull + (uint64_t)((k & 3) * 2), b, idesc, 1);
+            }
+        }
+        const long long t1 = clock64();
+        mma_commit(&bars[0]);
+        mbar_wait(&bars[0], 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tbase, 512);
+}
+}  // namespace tn
+
+extern "C" int tn_debug_mma_rate(int device, int nrep, int mode, uint32_t boff, long long *h_out2) {
+    tn::DeviceGuard g(device);
+    long long *d = nullptr;
+    TN_CUDA(cudaMalloc(&d, 16));
+    const int smem = 212992 + 128;
+    TN_CUDA(cudaFuncSetAttribute(tn::k_debug_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tn::k_debug_mma_rate<<<1, 160, smem>>>(d, nrep, mode, boff);
+    TN_CUDA(cudaDeviceSynchronize());
+    TN_CUDA(cudaMemcpy(h_out2, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return TN_OK;
+}

@@ -19,6 +19,8 @@
 
 namespace tn {
 
+static unsigned long long *g_timeline = nullptr;
+
 int launch_trace_internal(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
                           float *dist, uint32_t *verts, int dense, cudaStream_t s);
 
@@ -535,6 +537,7 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     TN_EV(4);
     MlpParams mf = mc;
     mf.S = S2; mf.vi = r->vi_f; mf.bary = r->bary_f; mf.dirbias = r->dirbias; mf.out = r->out_f;
+    mf.timeline = g_timeline;
     k_mlp<true><<<std::min<uint32_t>(tiles_f, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mf);
     TN_EV(5);
     k_composite<<<gridR, SAMPLE_WARPS * 32, smem_c, s>>>(p);
@@ -563,6 +566,9 @@ extern "C" int tn_render_get_timings(tn_tracer *h, float *ms6) {
     for (int i = 0; i < 6; ++i) TN_CUDA(cudaEventElapsedTime(&ms6[i], r->ev[i], r->ev[i + 1]));
     return TN_OK;
 }
+
+// debug: clock64 timeline of CTA 0 of the NEXT fine k_mlp launches (device buffer of >= 65001 u64, first word zeroed by caller)
+extern "C" int tn_debug_set_timeline(void *d_buf) { g_timeline = (unsigned long long *)d_buf; return TN_OK; }
 
 // test / debug hook: device pointers of the intermediate buffers of the last tn_render call
 extern "C" int tn_render_debug_buffers(tn_tracer *h, void **ptrs16) {

@@ -36,6 +36,10 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_test(bar, parity)) {}
 }
+// polite wait for many-warp consumers: back off between polls so that spinning does not eat issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    while (!mbar_test(bar, parity)) __nanosleep(ns);
+}
 
 // ---- TMA bulk copy global -> shared (1-D, no tensor map) -----------------------------------------
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
@@ -63,6 +67,16 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// same with a compile-time accumulate flag (no predicate register traffic in the issue loop)
+template <bool ACC>
+__device__ __forceinline__ void mma_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -124,10 +138,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ---- bf16 hi/lo split: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi) -----------------------------
 // packs elements (e0 -> bits [15:0], e1 -> bits [31:16]) so that element 2c sits in the low half of column c
 __device__ __forceinline__ void split_pack2(float e0, float e1, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(e0), h1 = __float2bfloat16_rn(e1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(e0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(e1 - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    uint32_t h, l;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(e1), "f"(e0));  // upper <- e1, lower <- e0
+    const float d0 = e0 - __uint_as_float(h << 16), d1 = e1 - __uint_as_float(h & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(d1), "f"(d0));
+    hi = h;
+    lo = l;
 }
 
 // byte offset of element (n, k) inside a [rows][64] bf16 block stored with the 128-byte swizzle
