@@ -59,6 +59,7 @@ int tn_destroy(tn_tracer *h) {
     tn::free_render(h);
     tn::free_mesh(h);
     cudaFree(h->d_flags);
+    cudaFree(h->d_ovf_list);
     delete h;
     return TN_OK;
 }

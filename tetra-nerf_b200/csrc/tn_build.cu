@@ -1,4 +1,4 @@
-// tn_build.cu -- load_tetrahedra: unique-face tables + on-device Morton-ordered 4-ary BVH.
+// tn_build.cu -- load_tetrahedra: unique-face tables + on-device Morton-ordered 8-ary BVH.
 //
 // Replaces TetrahedraStructure::build (src/tetrahedra_tracer.cpp:244-340): the reference converts the
 // 4T faces into unique triangles on the host (:45-71) and hands them to optixAccelBuild (:285-332).
@@ -159,7 +159,7 @@ __global__ void k_level(const float4 *__restrict__ child, uint32_t nchild, float
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nparent) return;
     float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-    for (uint32_t c = 4 * i; c < min(4 * i + 4, nchild); ++c) {
+    for (uint32_t c = TN_FAN * i; c < min(TN_FAN * i + TN_FAN, nchild); ++c) {
         const float4 a = child[2 * (size_t)c], b = child[2 * (size_t)c + 1];
         lo[0] = fminf(lo[0], a.x); lo[1] = fminf(lo[1], a.y); lo[2] = fminf(lo[2], a.z);
         hi[0] = fmaxf(hi[0], a.w); hi[1] = fmaxf(hi[1], b.x); hi[2] = fmaxf(hi[2], b.y);
@@ -223,13 +223,13 @@ int build_mesh(tn_tracer *h, const float *d_xyz, uint32_t V, const uint32_t *d_c
     for (;;) {
         if (L >= TN_MAX_LEVELS) { cleanup(); free_mesh(h); return fail(TN_ERR_ARG, "load_tetrahedra: too many BVH levels"); }
         lv.count[L] = cnt; lv.offset[L] = off;
-        off += (cnt + 3) & ~3u;  // keep every level's base a multiple of 4 nodes (128 B)
+        off += (cnt + TN_FAN - 1) & ~(TN_FAN - 1);  // keep every level's base a multiple of TN_FAN nodes (256 B)
         ++L;
         if (cnt == 1) break;
-        cnt = (cnt + 3) / 4;
+        cnt = (cnt + TN_FAN - 1) / TN_FAN;
     }
     if (L == 1) {  // a single tetrahedron: add a root above it so that traversal always starts at level >= 1
-        lv.count[1] = 1; lv.offset[1] = off; off += 4; L = 2;
+        lv.count[1] = 1; lv.offset[1] = off; off += TN_FAN; L = 2;
     }
     lv.nlevels = L;
     const uint32_t total_nodes = off;

@@ -34,10 +34,12 @@ struct DeviceGuard {
     }
 };
 
-// ---- acceleration structure: implicit 4-ary BVH over Morton-sorted tetrahedra ----------------
-// Level 0 = one node per tetrahedron (sorted order); node i of level l+1 bounds nodes 4i..4i+3 of
-// level l.  A node is 32 bytes: (lo.x lo.y lo.z hi.x)(hi.y hi.z - -).  All levels live in one array.
+// ---- acceleration structure: implicit 8-ary BVH over Morton-sorted tetrahedra ----------------
+// Level 0 = one node per tetrahedron (sorted order); node i of level l+1 bounds nodes 8i..8i+7 of
+// level l (256 contiguous bytes).  A node is 32 bytes: (lo.x lo.y lo.z hi.x)(hi.y hi.z - -).
+// All levels live in one array.
 constexpr int TN_MAX_LEVELS = 16;
+constexpr uint32_t TN_FAN = 8, TN_FAN_LOG2 = 3;
 struct BvhLevels {
     uint32_t count[TN_MAX_LEVELS];
     uint32_t offset[TN_MAX_LEVELS];  // in nodes
@@ -72,7 +74,9 @@ struct RenderState;
 struct tn_tracer {
     int device = 0;
     tn::Mesh mesh;
-    int *d_flags = nullptr;  // [0] traversal-stack overflow count
+    int *d_flags = nullptr;  // [0] traversal-stack overflow count, [2] number of rays deferred to the large-buffer pass
+    uint32_t *d_ovf_list = nullptr;  // rays deferred by phase 1 of trace_rays
+    uint32_t ovf_cap = 0;
     uint64_t launches = 0;
     tn::RenderState *render = nullptr;
 };
@@ -81,6 +85,7 @@ namespace tn {
 int build_mesh(tn_tracer *h, const float *d_xyz, uint32_t V, const uint32_t *d_cells, uint32_t T, cudaStream_t s);
 void free_mesh(tn_tracer *h);
 void free_render(tn_tracer *h);
+int launch_prefetch(tn_tracer *h, const void *const *extra, const size_t *extra_bytes, int nextra, cudaStream_t s);
 }  // namespace tn
 
 // =================================================================================================

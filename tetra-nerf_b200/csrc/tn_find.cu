@@ -1,6 +1,6 @@
 // tn_find.cu -- find_tetrahedra: point location by two closest-hit rays (+x / -x).
 // Replaces src/optix/optix_find_tetrahedra.cu:84-213 (+ FindTetrahedraPipeline, tetrahedra_tracer.cpp:589-853).
-// One thread per query point, depth-first walk of the 4-ary BVH with t-max shrinking; the closest hit
+// One thread per query point, depth-first walk of the 8-ary BVH with t-max shrinking; the closest hit
 // is the smallest (t, face id) key, as in oracle/tetra_oracle.cpp:orc_find_tetrahedra.
 #include "tn_common.cuh"
 
@@ -25,15 +25,15 @@ __device__ bool closest_hit(const FindParams &p, float ox, float oy, float oz, f
     const RaySetup rs = ray_setup(ox, oy, oz, dx, 0.f, 0.f);
     const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, 0.0f), iz = iy;
     const float pad = 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + p.absmax);
-    uint32_t stack[3 * TN_MAX_LEVELS + 4];
+    uint32_t stack[7 * TN_MAX_LEVELS + 8];
     int sp = 0;
     stack[sp++] = (uint32_t)(p.lv.nlevels - 1) << 28;
     u64 best = ~0ull;
     float bu = 0.f, bv = 0.f;
     while (sp) {
         const uint32_t e = stack[--sp];
-        const uint32_t cl = (e >> 28) - 1u, cbase = (e & 0x0FFFFFFFu) << 2;
-        const uint32_t nc = min(4u, p.lv.count[cl] - cbase);
+        const uint32_t cl = (e >> 28) - 1u, cbase = (e & 0x0FFFFFFFu) << TN_FAN_LOG2;
+        const uint32_t nc = min(TN_FAN, p.lv.count[cl] - cbase);
         for (uint32_t c = 0; c < nc; ++c) {
             const float4 *np = p.nodes + 2 * (size_t)(p.lv.offset[cl] + cbase + c);
             if (!slab(__ldg(np), __ldg(np + 1), ox, oy, oz, ix, iy, iz, pad)) continue;

@@ -500,6 +500,12 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     int rc = ensure_ws(r, R, M, Sc, S2);
     if (rc) return rc;
     TN_CUDA(cudaMemsetAsync(r->n_active, 0, 16, s));
+    {   // L2 warm-up of everything read-only that the step gathers from (mesh tables, field shadow, weight image)
+        const void *extra[2] = {r->fshadow, r->wimg};
+        const size_t extra_b[2] = {sizeof(float) * 64 * (size_t)r->V, 32768 + 3 * 65536};
+        rc = launch_prefetch(h, extra, extra_b, 2, s);
+        if (rc) return rc;
+    }
 #define TN_EV(i) do { if (r->profile) cudaEventRecord(r->ev[i], s); } while (0)
     TN_EV(0);
     rc = launch_trace_internal(h, d_origins, d_directions, R, M, r->num, r->cells, r->bary, r->dist, r->verts, 0, s);

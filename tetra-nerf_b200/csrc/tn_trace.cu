@@ -18,6 +18,8 @@
 //      identity and all lanes emit records in parallel; otherwise lane 0 runs the literal three-phase
 //      algorithm on the shared-memory keys and the lanes emit from its result.
 // More than M-1 hits: the M-1 smallest keys are kept (the reference keeps an arbitrary M-1).
+#include <algorithm>
+
 #include "tn_common.cuh"
 
 namespace tn {
@@ -43,6 +45,10 @@ struct TraceParams {
     int dense;
     int *flags;
     uint32_t hcap, scap, lcap;
+    // two-phase launch: phase 1 (small hit buffer, high occupancy) appends rays whose hits do not fit to
+    // `ovf_list` (count in ovf_count); phase 2 (ray_list != nullptr) re-traces exactly those with the full buffer
+    uint32_t *ovf_count, *ovf_list;
+    const uint32_t *ray_count, *ray_list;
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -161,7 +167,7 @@ __device__ uint32_t post_process_serial(u64 *key, uint2 *tts, uint32_t n, uint16
 }
 
 template <int MODE>  // 0: trace_rays (tetrahedra), 1: trace_rays_triangles (sorted raw face hits)
-__global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p) {
+__global__ void __launch_bounds__(TRACE_WARPS * 32, 7) k_trace(const TraceParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_count[TN_MAX_LEVELS], s_offset[TN_MAX_LEVELS];
     if (threadIdx.x < TN_MAX_LEVELS) { s_count[threadIdx.x] = p.lv.count[threadIdx.x]; s_offset[threadIdx.x] = p.lv.offset[threadIdx.x]; }
@@ -174,7 +180,9 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p)
     uint32_t *leafq = stack + p.scap;
     const uint32_t M = p.M;
 
-    for (uint32_t ray = blockIdx.x * TRACE_WARPS + warp; ray < p.R; ray += gridDim.x * TRACE_WARPS) {
+    const uint32_t nwork = p.ray_list ? *p.ray_count : p.R;
+    for (uint32_t wi = blockIdx.x * TRACE_WARPS + warp; wi < nwork; wi += gridDim.x * TRACE_WARPS) {
+        const uint32_t ray = p.ray_list ? p.ray_list[wi] : wi;
         const float ox = p.o[3 * (size_t)ray], oy = p.o[3 * (size_t)ray + 1], oz = p.o[3 * (size_t)ray + 2];
         const float dx = p.d[3 * (size_t)ray], dy = p.d[3 * (size_t)ray + 1], dz = p.d[3 * (size_t)ray + 2];
         const RaySetup rs = ray_setup(ox, oy, oz, dx, dy, dz);
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p)
 
         uint32_t sc = 0, lc = 0, nh = 0;
         u64 cutoff = ~0ull;
-        bool overflow = false;
+        bool overflow = false, deferred = false;
         if (rs.valid) {
             if (lane == 0) stack[0] = (uint32_t)(p.lv.nlevels - 1) << 28;
             sc = 1;
@@ -195,7 +203,9 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p)
             if (lc >= 32 || sc == 0) {
                 const uint32_t room = (p.hcap - nh) >> 2;
                 const uint32_t n = min(min(lc, 32u), room);
-                if (n == 0) {  // hit buffer full: nh > M-1 for sure, drop everything beyond the M-1 nearest
+                if (n == 0) {
+                    if (p.ovf_list != nullptr) { deferred = true; break; }  // phase 1: this ray needs the large buffer
+                    // hit buffer full: nh > M-1 for sure, drop everything beyond the M-1 nearest
                     cutoff = rank_select(hits, nh, M - 1, lane);
                     continue;
                 }
@@ -227,17 +237,17 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p)
                 lc -= n;
                 __syncwarp();
             } else {
-                const uint32_t n = min(min(sc, 32u), (p.scap - sc) / 3u);
-                if (n == 0) { overflow = true; break; }
+                const uint32_t n = min(min(sc, 32u), (p.scap - sc) / (TN_FAN - 1u));
+                if (n == 0) { if (p.ovf_list != nullptr) deferred = true; else overflow = true; break; }
                 uint32_t hm = 0, cl = 1, cbase = 0;
                 if (lane < n) {
                     const uint32_t e = stack[sc - 1 - lane];
                     cl = (e >> 28) - 1u;
-                    cbase = (e & 0x0FFFFFFFu) << 2;
-                    const uint32_t nc = min(4u, s_count[cl] - cbase);
+                    cbase = (e & 0x0FFFFFFFu) << TN_FAN_LOG2;
+                    const uint32_t nc = min(TN_FAN, s_count[cl] - cbase);
                     const float4 *np = p.nodes + 2 * (size_t)(s_offset[cl] + cbase);
 #pragma unroll
-                    for (uint32_t c = 0; c < 4; ++c) {
+                    for (uint32_t c = 0; c < TN_FAN; ++c) {
                         if (c < nc) {
                             const float4 a = __ldg(np + 2 * c), b = __ldg(np + 2 * c + 1);
                             if (slab(a, b, ox, oy, oz, ix, iy, iz, pad)) hm |= 1u << c;
@@ -252,10 +262,10 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p)
                 const uint32_t excl = incl - packed;
                 uint32_t sb = sc - n + (excl & 0xFFFFu), lb = lc + (excl >> 16);
 #pragma unroll
-                for (uint32_t c = 0; c < 4; ++c) {
+                for (uint32_t c = 0; c < TN_FAN; ++c) {
                     if (hm & (1u << c)) {
                         if (cl == 0) leafq[lb++] = cbase + c;
-                        else stack[sb++] = (cl << 28) | ((cbase + c) >> 0);
+                        else stack[sb++] = (cl << 28) | (cbase + c);
                     }
                 }
                 sc = sc - n + (total & 0xFFFFu);
@@ -263,11 +273,17 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p)
                 __syncwarp();
             }
         }
+        if (p.ovf_list != nullptr && nh > ((p.scap + p.lcap) >> 1)) deferred = true;  // tts staging: 8 bytes per hit
+        if (deferred) {  // uniform per warp
+            if (lane == 0) p.ovf_list[atomicAdd(p.ovf_count, 1u)] = ray;
+            __syncwarp();
+            continue;
+        }
         if (overflow) {
             if (lane == 0) atomicAdd(p.flags, 1);
             nh = 0;
         }
-        if (nh > M - 1) rank_select(hits, nh, M - 1, lane);
+        if (nh > M - 1) rank_select(hits, nh, M - 1, lane);  // (phase 1 never gets here with nh > hcap - 4 >= ... it defers first)
 
         // ---------------- 2. sort by (t, face id) ----------------
         if (nh > 1) bitonic_sort_keys(hits, nh, lane);
@@ -367,6 +383,47 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(const TraceParams p)
     }
 }
 
+// warm L2 with the read-only working set (BVH nodes, leaf records, face tables, vertices, ...): one bulk
+// prefetch instruction per 16 KB instead of thousands of latency-bound first-touch misses inside k_trace.
+struct PrefetchArgs {
+    const void *ptr[8];
+    unsigned long long bytes[8];
+    int n;
+};
+__global__ void k_l2_prefetch(const PrefetchArgs a) {
+    const unsigned long long CH = 16384ull;
+    unsigned long long base = 0;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+    for (int i = 0; i < a.n; ++i) {
+        const unsigned long long nch = (a.bytes[i] + CH - 1) / CH;
+        for (unsigned long long c = (tid + nth - base % nth) % nth; c < nch; c += nth) {
+            const unsigned long long off = c * CH;
+            const unsigned int sz = (unsigned int)min(CH, a.bytes[i] - off) & ~15u;
+            if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)a.ptr[i] + off), "r"(sz) : "memory");
+        }
+        base += nch;
+    }
+}
+
+int launch_prefetch(tn_tracer *h, const void *const *extra, const size_t *extra_bytes, int nextra, cudaStream_t s) {
+    const Mesh &m = h->mesh;
+    PrefetchArgs a{};
+    int n = 0;
+    auto add = [&](const void *p, size_t b) { if (p && b && n < 8 && ((uintptr_t)p & 15) == 0) { a.ptr[n] = p; a.bytes[n] = b; ++n; } };
+    uint32_t total_nodes = m.lv.offset[m.lv.nlevels - 1] + TN_FAN;
+    add(m.nodes, sizeof(float4) * 2 * (size_t)total_nodes);
+    add(m.leaves, sizeof(LeafRec) * (size_t)m.T);
+    add(m.tri, sizeof(uint4) * (size_t)m.F);
+    add(m.tt, sizeof(uint2) * (size_t)m.F);
+    add(m.xyz, sizeof(float) * 3 * (size_t)m.V);
+    for (int i = 0; i < nextra; ++i) add(extra[i], extra_bytes[i]);
+    a.n = n;
+    k_l2_prefetch<<<148, 128, 0, s>>>(a);
+    h->launches += 1;
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+
 static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells,
                         float *bary, float *dist, uint32_t *verts, int dense, cudaStream_t s) {
     if (!h) return fail(TN_ERR_ARG, "null tracer");
@@ -375,26 +432,47 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
     if (!h->mesh.nodes) return fail(TN_ERR_STATE, "trace_rays: no tetrahedra loaded (call load_tetrahedra first)");
     if (R == 0) return TN_OK;
     DeviceGuard g(h->device);
-    TraceParams p;
+    TraceParams p{};
     p.o = o; p.d = d; p.R = R; p.M = M; p.num = num; p.cells = cells; p.bary = bary; p.dist = dist; p.verts = verts;
     p.nodes = h->mesh.nodes; p.leaves = h->mesh.leaves; p.tri = (const uint4 *)h->mesh.tri; p.tt = (const uint2 *)h->mesh.tt;
     p.xyz = h->mesh.xyz; p.lv = h->mesh.lv; p.absmax = h->mesh.absmax; p.dense = dense; p.flags = h->d_flags;
-    p.hcap = M + 128;
-    p.scap = M > 512 ? 2 * M : 1024;
-    p.lcap = M > 512 ? M / 2 : 256;
-    const size_t smem = (size_t)TRACE_WARPS * ((size_t)p.hcap * 8 + (size_t)p.scap * 4 + (size_t)p.lcap * 4);
     auto kern = mode == 0 ? k_trace<0> : k_trace<1>;
-    TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int sms = 148, occ = 1;
+    int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    TN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TRACE_WARPS * 32, smem));
-    if (occ < 1) occ = 1;
+    auto launch = [&](uint32_t nblocks_wanted) -> int {
+        const size_t smem = (size_t)TRACE_WARPS * ((size_t)p.hcap * 8 + (size_t)p.scap * 4 + (size_t)p.lcap * 4);
+        TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        TN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TRACE_WARPS * 32, smem));
+        if (occ < 1) occ = 1;
+        const uint32_t grid = std::min<uint32_t>(nblocks_wanted, (uint32_t)(sms * occ));
+        kern<<<grid, TRACE_WARPS * 32, smem, s>>>(p);
+        h->launches += 1;
+        TN_CUDA(cudaGetLastError());
+        return TN_OK;
+    };
     const uint32_t want = (R + TRACE_WARPS - 1) / TRACE_WARPS;
-    const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sms * occ));
-    kern<<<grid, TRACE_WARPS * 32, smem, s>>>(p);
-    h->launches += 1;
-    TN_CUDA(cudaGetLastError());
-    return TN_OK;
+    if (M <= 256) {
+        // one launch: the hit buffer (M + 128 keys) is small enough for 28 rays in flight per SM
+        p.hcap = M + 128; p.scap = 640; p.lcap = 320;
+        return launch(want);
+    }
+    // phase 1: M keys per ray (7.75 KB of shared memory per ray -> 28 rays per SM); rays that fill it are deferred
+    if (h->ovf_cap < R) {
+        cudaFree(h->d_ovf_list);
+        h->d_ovf_list = nullptr; h->ovf_cap = 0;
+        TN_CUDA(cudaMalloc((void **)&h->d_ovf_list, sizeof(uint32_t) * (size_t)R));
+        h->ovf_cap = R;
+    }
+    uint32_t *ovf_count = reinterpret_cast<uint32_t *>(h->d_flags + 2);
+    TN_CUDA(cudaMemsetAsync(ovf_count, 0, sizeof(uint32_t), s));
+    p.hcap = M; p.scap = 640; p.lcap = 320; p.ovf_count = ovf_count; p.ovf_list = h->d_ovf_list;
+    int rc = launch(want);
+    if (rc) return rc;
+    // phase 2: the deferred rays with the full streaming buffer (M + 128 keys); exits at once when there are none
+    p.hcap = M + 128; p.scap = M > 512 ? 2 * M : 1024; p.lcap = M > 512 ? M / 2 : 320;
+    p.ovf_count = nullptr; p.ovf_list = nullptr; p.ray_count = ovf_count; p.ray_list = h->d_ovf_list;
+    return launch((uint32_t)sms);
 }
 
 int launch_trace_internal(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
