@@ -108,6 +108,9 @@ int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins,
  * mlp_fine, composite (used by bench.py for the roofline of the dominant kernel) */
 int tn_render_set_profiling(tn_tracer *h, int enable);
 int tn_render_get_timings(tn_tracer *h, float *ms6);
+/* out2[0] = 1 if the loaded mesh takes the adjacency-walk fast path (conforming, convex hull); out2[1] = rays of the last
+ * trace_rays call that needed the exact sort/pairing or all-hits stage.  Synchronises. */
+int tn_debug_trace_stats(tn_tracer *h, uint32_t *out2);
 /* ---- test hooks (not part of the reference surface) ------------------------------------------------
  * device pointers of the intermediate buffers of the last tn_render call, in the order
  * num, dist, n_active, ray_list, ebins_c, sbins_c, vi_c, bary_c, dens_c, ebins_f, vi_f, bary_f, out_f,

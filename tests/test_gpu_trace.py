@@ -193,3 +193,31 @@ def test_find_tetrahedra(cube_mesh, small_mesh):
     assert np.array_equal(out["barycentric_coordinates"].cpu().numpy().view(np.uint32), ref["barycentric_coordinates"].view(np.uint32))
     assert np.array_equal(out["valid_mask"].cpu().numpy(), ref["valid_mask"])
     assert 0.3 < ref["valid_mask"].mean() < 0.9
+
+
+def test_walk_fast_path_classification(small_mesh):
+    """the adjacency walk certifies most rays itself; the rest (sub-eps slivers, degenerate hits) go through the exact stage"""
+    V, C = small_mesh
+    tr = make_tracer(V, C)
+    o, d = syn.camera_rays(2000, seed=21)
+    g = gpu_trace(tr, o, d, 512)
+    walkable, listed = tr.trace_stats()
+    assert walkable and 0 <= listed < 0.15 * len(o), (walkable, listed)
+    assert_same(g, orc.OracleMesh(V, C).trace_rays(o, d, 512))
+
+
+def test_non_convex_mesh_takes_exact_path(small_mesh):
+    """remove tetrahedra from the hull -> non-convex hull: rays leave and re-enter; the reference pairs the two hull
+    faces of a gap into a record with cell = -1 (optix_trace_rays.cu:22-37: E == E).  Walk disabled, exact path used."""
+    V, C = small_mesh
+    cen = V[C].mean(1)
+    keep = ~((np.abs(cen[:, 0] - 0.5) < 0.12) & (cen[:, 1] < 0.6))  # carve a slot into the cloud
+    C2 = np.ascontiguousarray(C[keep])
+    tr = make_tracer(V, C2)
+    o, d = syn.camera_rays(600, seed=5)
+    g = gpu_trace(tr, o, d, 512)
+    walkable, _ = tr.trace_stats()
+    assert not walkable
+    ref = orc.OracleMesh(V, C2).trace_rays(o, d, 512)
+    assert_same(g, ref)
+    assert (ref["visited_cells"][np.arange(512)[None] < ref["num_visited_cells"][:, None]] == -1).any()  # gap records exist

@@ -60,6 +60,7 @@ int tn_destroy(tn_tracer *h) {
     tn::free_mesh(h);
     cudaFree(h->d_flags);
     cudaFree(h->d_ovf_list);
+    cudaFree(h->d_walk_keys);
     delete h;
     return TN_OK;
 }
@@ -103,5 +104,17 @@ int tn_get_faces(tn_tracer *h, uint32_t *d_tri, uint32_t *d_tt, void *stream) {
 }
 
 uint64_t tn_launch_count(tn_tracer *h) { return h ? h->launches : 0; }
+
+// test hook: (walkable mesh?, number of rays the last trace_rays call handed to the exact stage); synchronises the device
+int tn_debug_trace_stats(tn_tracer *h, uint32_t *out2) {
+    if (!h || !out2) return tn::fail(TN_ERR_ARG, "null argument");
+    tn::DeviceGuard g(h->device);
+    TN_CUDA(cudaDeviceSynchronize());
+    int flags[4];
+    TN_CUDA(cudaMemcpy(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+    out2[0] = h->mesh.walkable ? 1u : 0u;
+    out2[1] = (uint32_t)flags[2];
+    return TN_OK;
+}
 
 }  // extern "C"

@@ -47,11 +47,23 @@ struct BvhLevels {
 };
 
 // 64-byte leaf record of one tetrahedron, in sorted (Morton) order:
-//   v[j] = (x, y, z, bits(face_id_j | owner<<31)) ; face j is opposite vertex j and is stored in the
+//   v[j] = (x, y, z, bits(face_id_j | hull<<30 | owner<<31)) ; face j is opposite vertex j and is stored in the
 //   reference winding (v[(j+1)%4], v[(j+2)%4], v[(j+3)%4]) (src/tetrahedra_tracer.cpp:54-57) iff this
-//   tetrahedron is the face's first owner.
+//   tetrahedron is the face's first owner.  hull = the face has a single owner.
 struct LeafRec {
     float4 v[4];
+};
+#define TN_FACE_MASK 0x3FFFFFFFu
+#define TN_FACE_HULL 0x40000000u
+#define TN_FACE_OWNER 0x80000000u
+
+// 128-byte (one cache line) record of one tetrahedron, indexed by tetrahedron id, for the adjacency walk:
+struct WalkRec {
+    float4 v[4];       // as LeafRec
+    uint32_t nbr[4];   // tetrahedron across face j (TN_EMPTY on the hull)
+    uint32_t vid[4];   // the cell's vertex ids
+    uint32_t wind;     // 4 x 6 bits: stored winding of face j as three local vertex indices (2 bits each, a | b<<2 | c<<4)
+    uint32_t pad[7];
 };
 
 struct Mesh {
@@ -63,6 +75,14 @@ struct Mesh {
     float4 *nodes = nullptr;         // BVH nodes, 2 float4 per node
     LeafRec *leaves = nullptr;       // [T]
     uint32_t *leaf_tet = nullptr;    // [T] sorted position -> tetrahedron id
+    // adjacency walk (fast path of trace_rays): valid when `walkable`
+    WalkRec *walk = nullptr;         // [T]
+    float4 *hull_nodes = nullptr;    // BVH over the tetrahedra that own a hull face
+    LeafRec *hull_leaves = nullptr;  // [H]
+    uint32_t *hull_tet = nullptr;    // [H] sorted position -> tetrahedron id
+    BvhLevels hull_lv{};
+    uint32_t H = 0;
+    bool walkable = false;           // conforming mesh with a convex hull (always true for a Delaunay triangulation)
     BvhLevels lv{};
     float absmax = 0.f;              // max |coordinate| over the vertices
 };
@@ -75,8 +95,10 @@ struct tn_tracer {
     int device = 0;
     tn::Mesh mesh;
     int *d_flags = nullptr;  // [0] traversal-stack overflow count, [2] number of rays deferred to the large-buffer pass
-    uint32_t *d_ovf_list = nullptr;  // rays deferred by phase 1 of trace_rays
+    uint32_t *d_ovf_list = nullptr;  // rays deferred by phase 1 of trace_rays / listed by the walk for the exact stage
     uint32_t ovf_cap = 0;
+    unsigned long long *d_walk_keys = nullptr;  // [R, M] (t, face) keys written by the adjacency walk
+    size_t walk_keys_cap = 0;
     uint64_t launches = 0;
     tn::RenderState *render = nullptr;
 };
@@ -85,6 +107,10 @@ namespace tn {
 int build_mesh(tn_tracer *h, const float *d_xyz, uint32_t V, const uint32_t *d_cells, uint32_t T, cudaStream_t s);
 void free_mesh(tn_tracer *h);
 void free_render(tn_tracer *h);
+int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
+                float *dist, uint32_t *verts, unsigned long long *keys, uint32_t *list, uint32_t *list_count, cudaStream_t s);
+int launch_tail_fill(tn_tracer *h, uint32_t R, uint32_t M, const uint32_t *num, uint32_t *cells, float *bary, float *dist, uint32_t *verts,
+                     cudaStream_t s);
 int launch_prefetch(tn_tracer *h, const void *const *extra, const size_t *extra_bytes, int nextra, cudaStream_t s);
 }  // namespace tn
 

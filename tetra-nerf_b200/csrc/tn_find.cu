@@ -45,10 +45,10 @@ __device__ bool closest_hit(const FindParams &p, float ox, float oy, float oz, f
             const uint32_t f[4] = {__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w), __float_as_uint(v3.w)};
             float tt_, uu, vv;
             u64 k;
-            if ((f[0] >> 31) && tri_test(s1, s2, s3, tt_, uu, vv)) { k = ((u64)__float_as_uint(tt_) << 32) | (f[0] & 0x7FFFFFFFu); if (k < best) { best = k; bu = uu; bv = vv; } }
-            if ((f[1] >> 31) && tri_test(s2, s3, s0, tt_, uu, vv)) { k = ((u64)__float_as_uint(tt_) << 32) | (f[1] & 0x7FFFFFFFu); if (k < best) { best = k; bu = uu; bv = vv; } }
-            if ((f[2] >> 31) && tri_test(s3, s0, s1, tt_, uu, vv)) { k = ((u64)__float_as_uint(tt_) << 32) | (f[2] & 0x7FFFFFFFu); if (k < best) { best = k; bu = uu; bv = vv; } }
-            if ((f[3] >> 31) && tri_test(s0, s1, s2, tt_, uu, vv)) { k = ((u64)__float_as_uint(tt_) << 32) | (f[3] & 0x7FFFFFFFu); if (k < best) { best = k; bu = uu; bv = vv; } }
+            if ((f[0] >> 31) && tri_test(s1, s2, s3, tt_, uu, vv)) { k = ((u64)__float_as_uint(tt_) << 32) | (f[0] & TN_FACE_MASK); if (k < best) { best = k; bu = uu; bv = vv; } }
+            if ((f[1] >> 31) && tri_test(s2, s3, s0, tt_, uu, vv)) { k = ((u64)__float_as_uint(tt_) << 32) | (f[1] & TN_FACE_MASK); if (k < best) { best = k; bu = uu; bv = vv; } }
+            if ((f[2] >> 31) && tri_test(s3, s0, s1, tt_, uu, vv)) { k = ((u64)__float_as_uint(tt_) << 32) | (f[2] & TN_FACE_MASK); if (k < best) { best = k; bu = uu; bv = vv; } }
+            if ((f[3] >> 31) && tri_test(s0, s1, s2, tt_, uu, vv)) { k = ((u64)__float_as_uint(tt_) << 32) | (f[3] & TN_FACE_MASK); if (k < best) { best = k; bu = uu; bv = vv; } }
         }
     }
     if (best == ~0ull) return false;

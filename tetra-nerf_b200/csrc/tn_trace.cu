@@ -49,6 +49,9 @@ struct TraceParams {
     // `ovf_list` (count in ovf_count); phase 2 (ray_list != nullptr) re-traces exactly those with the full buffer
     uint32_t *ovf_count, *ovf_list;
     const uint32_t *ray_count, *ray_list;
+    // list entries with bit 31 set carry their face hits already (written by the adjacency walk, tn_walk.cu):
+    // num[ray] keys at keys_in[ray*M ..]; the gather is skipped and only sort + pairing + emit run
+    const u64 *keys_in;
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -182,7 +185,9 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 7) k_trace(const TraceParams
 
     const uint32_t nwork = p.ray_list ? *p.ray_count : p.R;
     for (uint32_t wi = blockIdx.x * TRACE_WARPS + warp; wi < nwork; wi += gridDim.x * TRACE_WARPS) {
-        const uint32_t ray = p.ray_list ? p.ray_list[wi] : wi;
+        const uint32_t entry = p.ray_list ? p.ray_list[wi] : wi;
+        const uint32_t ray = entry & 0x7FFFFFFFu;
+        const bool provided = p.keys_in != nullptr && (entry >> 31) != 0u;
         const float ox = p.o[3 * (size_t)ray], oy = p.o[3 * (size_t)ray + 1], oz = p.o[3 * (size_t)ray + 2];
         const float dx = p.d[3 * (size_t)ray], dy = p.d[3 * (size_t)ray + 1], dz = p.d[3 * (size_t)ray + 2];
         const RaySetup rs = ray_setup(ox, oy, oz, dx, dy, dz);
@@ -192,7 +197,10 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 7) k_trace(const TraceParams
         uint32_t sc = 0, lc = 0, nh = 0;
         u64 cutoff = ~0ull;
         bool overflow = false, deferred = false;
-        if (rs.valid) {
+        if (provided) {
+            nh = p.num[ray];
+            for (uint32_t i = lane; i < nh; i += 32) hits[i] = p.keys_in[(size_t)ray * M + i];
+        } else if (rs.valid) {
             if (lane == 0) stack[0] = (uint32_t)(p.lv.nlevels - 1) << 28;
             sc = 1;
         }
@@ -220,10 +228,10 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 7) k_trace(const TraceParams
                     const uint32_t f0 = __float_as_uint(v0.w), f1 = __float_as_uint(v1.w), f2 = __float_as_uint(v2.w), f3 = __float_as_uint(v3.w);
                     float t, u, v;
                     // face j = (v[(j+1)&3], v[(j+2)&3], v[(j+3)&3])   (src/tetrahedra_tracer.cpp:54-57)
-                    if ((f0 >> 31) && tri_test(s1, s2, s3, t, u, v)) { k0 = ((u64)__float_as_uint(t) << 32) | (f0 & 0x7FFFFFFFu); if (k0 < cutoff) fl |= 1u; }
-                    if ((f1 >> 31) && tri_test(s2, s3, s0, t, u, v)) { k1 = ((u64)__float_as_uint(t) << 32) | (f1 & 0x7FFFFFFFu); if (k1 < cutoff) fl |= 2u; }
-                    if ((f2 >> 31) && tri_test(s3, s0, s1, t, u, v)) { k2 = ((u64)__float_as_uint(t) << 32) | (f2 & 0x7FFFFFFFu); if (k2 < cutoff) fl |= 4u; }
-                    if ((f3 >> 31) && tri_test(s0, s1, s2, t, u, v)) { k3 = ((u64)__float_as_uint(t) << 32) | (f3 & 0x7FFFFFFFu); if (k3 < cutoff) fl |= 8u; }
+                    if ((f0 >> 31) && tri_test(s1, s2, s3, t, u, v)) { k0 = ((u64)__float_as_uint(t) << 32) | (f0 & TN_FACE_MASK); if (k0 < cutoff) fl |= 1u; }
+                    if ((f1 >> 31) && tri_test(s2, s3, s0, t, u, v)) { k1 = ((u64)__float_as_uint(t) << 32) | (f1 & TN_FACE_MASK); if (k1 < cutoff) fl |= 2u; }
+                    if ((f2 >> 31) && tri_test(s3, s0, s1, t, u, v)) { k2 = ((u64)__float_as_uint(t) << 32) | (f2 & TN_FACE_MASK); if (k2 < cutoff) fl |= 4u; }
+                    if ((f3 >> 31) && tri_test(s0, s1, s2, t, u, v)) { k3 = ((u64)__float_as_uint(t) << 32) | (f3 & TN_FACE_MASK); if (k3 < cutoff) fl |= 8u; }
                 }
                 const uint32_t c = __popc(fl);
                 const uint32_t incl = warp_incl_scan(c, lane);
@@ -410,9 +418,15 @@ int launch_prefetch(tn_tracer *h, const void *const *extra, const size_t *extra_
     PrefetchArgs a{};
     int n = 0;
     auto add = [&](const void *p, size_t b) { if (p && b && n < 8 && ((uintptr_t)p & 15) == 0) { a.ptr[n] = p; a.bytes[n] = b; ++n; } };
-    uint32_t total_nodes = m.lv.offset[m.lv.nlevels - 1] + TN_FAN;
-    add(m.nodes, sizeof(float4) * 2 * (size_t)total_nodes);
-    add(m.leaves, sizeof(LeafRec) * (size_t)m.T);
+    if (m.walkable) {  // the walk touches one 128-byte record per crossed tetrahedron; the big BVH is only the rare exact path's
+        add(m.walk, sizeof(WalkRec) * (size_t)m.T);
+        add(m.hull_leaves, sizeof(LeafRec) * (size_t)m.H);
+        add(m.hull_nodes, sizeof(float4) * 2 * (size_t)(m.hull_lv.offset[m.hull_lv.nlevels - 1] + TN_FAN));
+    } else {
+        const uint32_t total_nodes = m.lv.offset[m.lv.nlevels - 1] + TN_FAN;
+        add(m.nodes, sizeof(float4) * 2 * (size_t)total_nodes);
+        add(m.leaves, sizeof(LeafRec) * (size_t)m.T);
+    }
     add(m.tri, sizeof(uint4) * (size_t)m.F);
     add(m.tt, sizeof(uint2) * (size_t)m.F);
     add(m.xyz, sizeof(float) * 3 * (size_t)m.V);
@@ -452,6 +466,33 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
         return TN_OK;
     };
     const uint32_t want = (R + TRACE_WARPS - 1) / TRACE_WARPS;
+    if (mode == 0 && h->mesh.walkable && M >= 4) {
+        // fast path: adjacency walk (tn_walk.cu); rays it cannot certify are listed for the exact stage below
+        const size_t need = (size_t)R * M;
+        if (h->walk_keys_cap < need) {
+            cudaFree(h->d_walk_keys);
+            h->d_walk_keys = nullptr; h->walk_keys_cap = 0;
+            TN_CUDA(cudaMalloc((void **)&h->d_walk_keys, sizeof(u64) * need));
+            h->walk_keys_cap = need;
+        }
+        if (h->ovf_cap < R) {
+            cudaFree(h->d_ovf_list);
+            h->d_ovf_list = nullptr; h->ovf_cap = 0;
+            TN_CUDA(cudaMalloc((void **)&h->d_ovf_list, sizeof(uint32_t) * (size_t)R));
+            h->ovf_cap = R;
+        }
+        uint32_t *list_count = reinterpret_cast<uint32_t *>(h->d_flags + 2);
+        TN_CUDA(cudaMemsetAsync(list_count, 0, sizeof(uint32_t), s));
+        int rc = launch_walk(h, o, d, R, M, num, cells, bary, dist, verts, h->d_walk_keys, h->d_ovf_list, list_count, s);
+        if (rc) return rc;
+        p.dense = 0;
+        p.hcap = M + 128; p.scap = M > 512 ? 2 * M : 1024; p.lcap = M > 512 ? M / 2 : 320;
+        p.ray_count = list_count; p.ray_list = h->d_ovf_list; p.keys_in = h->d_walk_keys;
+        rc = launch((uint32_t)sms);
+        if (rc) return rc;
+        if (dense) return launch_tail_fill(h, R, M, num, cells, bary, dist, verts, s);
+        return TN_OK;
+    }
     if (M <= 256) {
         // one launch: the hit buffer (M + 128 keys) is small enough for 28 rays in flight per SM
         p.hcap = M + 128; p.scap = 640; p.lcap = 320;

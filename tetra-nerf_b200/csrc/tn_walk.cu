@@ -1,0 +1,188 @@
+// tn_walk.cu -- fast path of trace_rays: adjacency walk through the tetrahedral mesh, one thread per ray.
+//
+// The reference gathers every face hit of a ray with an OptiX any-hit program, sorts them and pairs consecutive
+// faces (src/optix/optix_trace_rays.cu:268-331).  In a conforming mesh with a convex hull (every Delaunay
+// triangulation) the hit faces of a generic ray are exactly the faces crossed when walking tetrahedron to
+// tetrahedron from the hull entry face, already in order -- ~40x fewer instructions per ray than the all-hits BVH
+// gather of tn_trace.cu.  Bit-exactness with the oracle is kept by construction and by classification:
+//   * every face is tested in its stored winding (WalkRec::wind) with the same watertight fp32 test, so (t,u,v) are
+//     the bits the exact path computes;
+//   * a ray is emitted directly ("generic") only if every step found exactly ONE exit face and consecutive hits
+//     are >= eps apart -- then the reference's dedupe phase is a no-op and its pairing is the identity;
+//   * a ray that met a crossing shorter than eps keeps its (t, face) key list; the exact sort + literal pairing
+//     stage of tn_trace.cu runs on that list (mode "keys provided");
+//   * anything else (zero or several exit faces: edge/vertex hits; origin inside the mesh) is re-traced by the
+//     exact all-hits path.  Meshes that are not walkable (non-convex hull) never take this path.
+#include "tn_common.cuh"
+
+namespace tn {
+typedef unsigned long long u64;
+#define TN_EPS 1e-6f
+
+struct WalkParams {
+    const float *o, *d;
+    uint32_t R, M;
+    uint32_t *num, *cells;
+    float *bary, *dist;
+    uint32_t *verts;
+    const WalkRec *walk;
+    const float4 *hull_nodes;
+    const LeafRec *hull_leaves;
+    const uint32_t *hull_tet;
+    BvhLevels hlv;
+    float absmax;
+    u64 *keys;              // [R, M] (t bits << 32 | face) in walk order
+    uint32_t *list, *list_count;  // rays for the exact stage: ray | 0x80000000 = keys provided
+};
+
+__global__ void __launch_bounds__(64) k_walk(const WalkParams p) {
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= p.R) return;
+    const float ox = p.o[3 * (size_t)ray], oy = p.o[3 * (size_t)ray + 1], oz = p.o[3 * (size_t)ray + 2];
+    const float dx = p.d[3 * (size_t)ray], dy = p.d[3 * (size_t)ray + 1], dz = p.d[3 * (size_t)ray + 2];
+    const RaySetup rs = ray_setup(ox, oy, oz, dx, dy, dz);
+    if (!rs.valid) { p.num[ray] = 0; return; }
+    const size_t row = (size_t)ray * p.M;
+
+    // ---- hull entry: closest hit over the hull faces (smallest (t, face id) key) ----
+    u64 best = ~0ull;
+    float bu = 0.f, bv = 0.f;
+    uint32_t btet = TN_EMPTY, bj = 0;
+    {
+        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+        const float pad = 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + p.absmax);
+        uint32_t stack[7 * TN_MAX_LEVELS + 8];
+        int sp = 0;
+        stack[sp++] = (uint32_t)(p.hlv.nlevels - 1) << 28;
+        while (sp) {
+            const uint32_t e = stack[--sp];
+            const uint32_t cl = (e >> 28) - 1u, cbase = (e & 0x0FFFFFFFu) << TN_FAN_LOG2;
+            const uint32_t nc = min(TN_FAN, p.hlv.count[cl] - cbase);
+            for (uint32_t c = 0; c < nc; ++c) {
+                const float4 *np = p.hull_nodes + 2 * (size_t)(p.hlv.offset[cl] + cbase + c);
+                if (!slab(__ldg(np), __ldg(np + 1), ox, oy, oz, ix, iy, iz, pad)) continue;
+                if (cl != 0) { stack[sp++] = (cl << 28) | (cbase + c); continue; }
+                const float4 *lp = reinterpret_cast<const float4 *>(p.hull_leaves + cbase + c);
+                const float4 v0 = __ldg(lp), v1 = __ldg(lp + 1), v2 = __ldg(lp + 2), v3 = __ldg(lp + 3);
+                const uint32_t f[4] = {__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w), __float_as_uint(v3.w)};
+                if (!((f[0] | f[1] | f[2] | f[3]) & TN_FACE_HULL)) continue;
+                const Sheared s[4] = {shear(rs, v0.x, v0.y, v0.z), shear(rs, v1.x, v1.y, v1.z), shear(rs, v2.x, v2.y, v2.z), shear(rs, v3.x, v3.y, v3.z)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!(f[j] & TN_FACE_HULL)) continue;
+                    float t, u, v;  // a hull face is always owned: its stored winding is this rotation
+                    if (tri_test(s[(j + 1) & 3], s[(j + 2) & 3], s[(j + 3) & 3], t, u, v)) {
+                        const u64 k = ((u64)__float_as_uint(t) << 32) | (f[j] & TN_FACE_MASK);
+                        if (k < best) { best = k; bu = u; bv = v; btet = p.hull_tet[cbase + c]; bj = (uint32_t)j; }
+                    }
+                }
+            }
+        }
+    }
+    if (btet == TN_EMPTY) { p.num[ray] = 0; return; }  // the ray misses the mesh
+
+    // ---- walk ----
+    uint32_t c = btet, jin = bj, fin = (uint32_t)best, nfaces = 1, nrec = 0;
+    float t_in = __uint_as_float((uint32_t)(best >> 32)), u_in = bu, v_in = bv;
+    bool generic = true, exact = false;
+    p.keys[row] = best;
+    for (;;) {
+        const float4 *wp = reinterpret_cast<const float4 *>(p.walk + c);
+        const float4 v0 = __ldg(wp), v1 = __ldg(wp + 1), v2 = __ldg(wp + 2), v3 = __ldg(wp + 3);
+        const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(wp + 4));
+        const uint4 vid = __ldg(reinterpret_cast<const uint4 *>(wp + 5));
+        const uint32_t wind = __ldg(reinterpret_cast<const uint32_t *>(wp + 6));
+        const uint32_t fw[4] = {__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w), __float_as_uint(v3.w)};
+        if (nrec != 0 || true) {  // locate the entry face inside this tetrahedron (after the first step it is the shared face)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((fw[j] & TN_FACE_MASK) == fin) jin = (uint32_t)j;
+        }
+        const Sheared s[4] = {shear(rs, v0.x, v0.y, v0.z), shear(rs, v1.x, v1.y, v1.z), shear(rs, v2.x, v2.y, v2.z), shear(rs, v3.x, v3.y, v3.z)};
+        uint32_t hits = 0, jout = 0;
+        float t_out = 0.f, u_out = 0.f, v_out = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((uint32_t)j == jin) continue;
+            const uint32_t w = (wind >> (6 * j)) & 63u;
+            float t, u, v;
+            if (tri_test(s[w & 3u], s[(w >> 2) & 3u], s[(w >> 4) & 3u], t, u, v)) { hits++; jout = (uint32_t)j; t_out = t; u_out = u; v_out = v; }
+        }
+        if (hits != 1) { exact = true; break; }
+        const uint32_t fout = fw[jout] & TN_FACE_MASK;
+        if (t_out < t_in || fabsf(__fsub_rn(t_out, t_in)) < TN_EPS) generic = false;
+        if (generic) {
+            // record (optix_trace_rays.cu:216-225 with combine_indices :39-75), expressed in local vertex indices
+            const uint32_t vv[4] = {vid.x, vid.y, vid.z, vid.w};
+            const uint32_t wi = (wind >> (6 * jin)) & 63u, wo = (wind >> (6 * jout)) & 63u;
+            const uint32_t ia[3] = {wi & 3u, (wi >> 2) & 3u, (wi >> 4) & 3u}, oa[3] = {wo & 3u, (wo >> 2) & 3u, (wo >> 4) & 3u};
+            const float r2[3] = {__fsub_rn(__fsub_rn(1.0f, u_out), v_out), u_out, v_out};
+            float o2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (ia[q] == oa[i]) o2[q] = r2[i];
+            const size_t g = row + nrec;
+            p.cells[g] = c;
+            reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(vv[jin], vv[ia[0]], vv[ia[1]], vv[ia[2]]);
+            float2 *bp = reinterpret_cast<float2 *>(p.bary + 6 * g);
+            bp[0] = make_float2(__fsub_rn(__fsub_rn(1.0f, u_in), v_in), u_in);
+            bp[1] = make_float2(v_in, o2[0]);
+            bp[2] = make_float2(o2[1], o2[2]);
+            reinterpret_cast<float2 *>(p.dist)[g] = make_float2(t_in, t_out);
+        }
+        p.keys[row + nfaces] = ((u64)__float_as_uint(t_out) << 32) | fout;
+        nfaces++;
+        nrec++;
+        const uint32_t nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+        const uint32_t next = nbv[jout];
+        if (next == TN_EMPTY || nfaces >= p.M - 1) break;  // left the mesh, or the M-1 nearest faces are in (optix_trace_rays.cu:312-315)
+        c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out;
+    }
+    if (exact) {
+        p.list[atomicAdd(p.list_count, 1u)] = ray;
+        p.num[ray] = 0;
+    } else if (!generic) {
+        p.list[atomicAdd(p.list_count, 1u)] = ray | 0x80000000u;
+        p.num[ray] = nfaces;  // number of keys; the pairing stage replaces it by the number of records
+    } else {
+        p.num[ray] = nrec;
+    }
+}
+
+// dense API tails (optix_trace_rays.cu:260-265 + the zeroed scratch tails pinned by the oracle): one warp per ray
+__global__ void k_tail_fill(uint32_t R, uint32_t M, const uint32_t *__restrict__ num, uint32_t *__restrict__ cells, float *__restrict__ bary,
+                            float *__restrict__ dist, uint32_t *__restrict__ verts) {
+    const uint32_t ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= R) return;
+    const size_t row = (size_t)ray * M;
+    for (uint32_t j = num[ray] + lane; j < M; j += 32) {
+        const size_t g = row + j;
+        cells[g] = TN_EMPTY;
+        reinterpret_cast<uint4 *>(verts)[g] = make_uint4(TN_EMPTY, TN_EMPTY, TN_EMPTY, TN_EMPTY);
+        float2 *bp = reinterpret_cast<float2 *>(bary + 6 * g);
+        bp[0] = make_float2(0.f, 0.f); bp[1] = make_float2(0.f, 0.f); bp[2] = make_float2(0.f, 0.f);
+        reinterpret_cast<float2 *>(dist)[g] = make_float2(0.f, 0.f);
+    }
+}
+
+int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
+                float *dist, uint32_t *verts, u64 *keys, uint32_t *list, uint32_t *list_count, cudaStream_t s) {
+    WalkParams p{};
+    p.o = o; p.d = d; p.R = R; p.M = M; p.num = num; p.cells = cells; p.bary = bary; p.dist = dist; p.verts = verts;
+    p.walk = h->mesh.walk; p.hull_nodes = h->mesh.hull_nodes; p.hull_leaves = h->mesh.hull_leaves; p.hull_tet = h->mesh.hull_tet;
+    p.hlv = h->mesh.hull_lv; p.absmax = h->mesh.absmax; p.keys = keys; p.list = list; p.list_count = list_count;
+    k_walk<<<(R + 63) / 64, 64, 0, s>>>(p);
+    h->launches += 1;
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+int launch_tail_fill(tn_tracer *h, uint32_t R, uint32_t M, const uint32_t *num, uint32_t *cells, float *bary, float *dist, uint32_t *verts,
+                     cudaStream_t s) {
+    k_tail_fill<<<(uint32_t)(((size_t)R * 32 + 255) / 256), 256, 0, s>>>(R, M, num, cells, bary, dist, verts);
+    h->launches += 1;
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+}  // namespace tn

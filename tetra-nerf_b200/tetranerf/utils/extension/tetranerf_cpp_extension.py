@@ -34,6 +34,7 @@ _lib.tn_find_tetrahedra.argtypes = [_vp, _vp, _u32, _vp, _vp, _vp, _vp]
 _lib.tn_find_visited_cells.argtypes = [_vp, _u32, _u32, _u32] + [_vp] * 11
 _lib.tn_interpolate_values.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]
 _lib.tn_interpolate_values_backward.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]
+_lib.tn_debug_trace_stats.argtypes = [_vp, C.POINTER(_u32)]
 _lib.tn_launch_count.restype = C.c_uint64
 _lib.tn_launch_count.argtypes = [_vp]
 
@@ -133,6 +134,12 @@ class TetrahedraTracer:
         """Stream sync + deferred device-side error check (the reference syncs on every call,
         src/tetrahedra_tracer.cpp:173-174; here it is explicit)."""
         _check(_lib.tn_synchronize(self._h, _stream(self._device)))
+
+    def trace_stats(self):
+        """(walkable mesh?, rays of the last trace_rays that took the exact stage) -- test/diagnostic hook"""
+        out = (_u32 * 2)()
+        _check(_lib.tn_debug_trace_stats(self._h, out))
+        return bool(out[0]), int(out[1])
 
     def launch_count(self) -> int:
         return int(_lib.tn_launch_count(self._h))
