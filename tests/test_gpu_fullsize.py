@@ -70,6 +70,15 @@ def test_full_size_permutation_invariance_and_determinism(scene):
     out2 = tr.trace_rays(torch.from_numpy(o[perm]).to(DEV), torch.from_numpy(d[perm]).to(DEV), 512)
     for k in KEYS:
         assert np.array_equal(out2[k].cpu().numpy(), out[k][perm]), k
+    # the other implementation of trace_rays (adjacency walk) gives the same bits at full size
+    tr.set_walk_min_rays(0)
+    out3 = tr.trace_rays(torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), 512)
+    tr.synchronize()
+    walkable, listed = tr.trace_stats()
+    tr.set_walk_min_rays(10240)
+    assert walkable and listed < 0.15 * len(o)
+    for k in KEYS:
+        assert np.array_equal(out3[k].cpu().numpy(), out[k]), k
 
 
 def test_full_size_render(scene):

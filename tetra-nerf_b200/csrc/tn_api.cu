@@ -105,6 +105,15 @@ int tn_get_faces(tn_tracer *h, uint32_t *d_tri, uint32_t *d_tt, void *stream) {
 
 uint64_t tn_launch_count(tn_tracer *h) { return h ? h->launches : 0; }
 
+// batches with at least `n` rays take the adjacency-walk fast path of trace_rays (0 = always, UINT32_MAX = never);
+// measured crossover on B200 / 302k tetrahedra: ~10k rays (profiles/r1_trace_sweep.json)
+extern "C" int tn_set_walk_min_rays(tn_tracer *h, uint32_t n) {
+    if (!h) return tn::fail(TN_ERR_ARG, "null tracer");
+    h->walk_min_rays = n;
+    return TN_OK;
+}
+static uint32_t g_last_exact = 0;
+extern "C" uint32_t tn_debug_last_exact_count(void) { return g_last_exact; }
 // test hook: (walkable mesh?, number of rays the last trace_rays call handed to the exact stage); synchronises the device
 int tn_debug_trace_stats(tn_tracer *h, uint32_t *out2) {
     if (!h || !out2) return tn::fail(TN_ERR_ARG, "null argument");
@@ -114,6 +123,7 @@ int tn_debug_trace_stats(tn_tracer *h, uint32_t *out2) {
     TN_CUDA(cudaMemcpy(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost));
     out2[0] = h->mesh.walkable ? 1u : 0u;
     out2[1] = (uint32_t)flags[2];
+    g_last_exact = (uint32_t)flags[3];
     return TN_OK;
 }
 

@@ -99,6 +99,7 @@ struct tn_tracer {
     uint32_t ovf_cap = 0;
     unsigned long long *d_walk_keys = nullptr;  // [R, M] (t, face) keys written by the adjacency walk
     size_t walk_keys_cap = 0;
+    uint32_t walk_min_rays = 10240;  // batches at least this large take the adjacency-walk fast path (see launch_trace)
     uint64_t launches = 0;
     tn::RenderState *render = nullptr;
 };

@@ -19,6 +19,7 @@
 //      algorithm on the shared-memory keys and the lanes emit from its result.
 // More than M-1 hits: the M-1 smallest keys are kept (the reference keeps an arbitrary M-1).
 #include <algorithm>
+#include <cstdlib>
 
 #include "tn_common.cuh"
 
@@ -466,7 +467,12 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
         return TN_OK;
     };
     const uint32_t want = (R + TRACE_WARPS - 1) / TRACE_WARPS;
-    if (mode == 0 && h->mesh.walkable && M >= 4) {
+    // path choice: the adjacency walk needs ~5x fewer instructions per ray but runs one thread per ray, so it only pays
+    // once there are enough rays to fill the machine; small batches are latency-bound and use the warp-per-ray gather.
+    // TETRANERF_B200_WALK=0/1 forces the choice (tests exercise both), default: walk when R >= walk_min_rays.
+    static const int walk_env = [] { const char *e = getenv("TETRANERF_B200_WALK"); return e ? atoi(e) : -1; }();
+    const bool use_walk = walk_env >= 0 ? walk_env != 0 : R >= h->walk_min_rays;
+    if (mode == 0 && h->mesh.walkable && M >= 4 && use_walk) {
         // fast path: adjacency walk (tn_walk.cu); rays it cannot certify are listed for the exact stage below
         const size_t need = (size_t)R * M;
         if (h->walk_keys_cap < need) {
@@ -482,7 +488,7 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
             h->ovf_cap = R;
         }
         uint32_t *list_count = reinterpret_cast<uint32_t *>(h->d_flags + 2);
-        TN_CUDA(cudaMemsetAsync(list_count, 0, sizeof(uint32_t), s));
+        TN_CUDA(cudaMemsetAsync(list_count, 0, 2 * sizeof(uint32_t), s));
         int rc = launch_walk(h, o, d, R, M, num, cells, bary, dist, verts, h->d_walk_keys, h->d_ovf_list, list_count, s);
         if (rc) return rc;
         p.dense = 0;

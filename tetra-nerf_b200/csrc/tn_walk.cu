@@ -35,7 +35,14 @@ struct WalkParams {
     uint32_t *list, *list_count;  // rays for the exact stage: ray | 0x80000000 = keys provided
 };
 
-__global__ void __launch_bounds__(64) k_walk(const WalkParams p) {
+constexpr int WALK_THREADS = 32;
+__device__ __forceinline__ uint32_t sel4u(uint32_t k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
+
+__global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams p) {
+    // sheared vertices of the current tetrahedron, one column per thread: the stored winding of a face selects three of
+    // the four vertices at run time, which would force a register array into local memory; shared memory indexes freely
+    __shared__ float ssm[12][WALK_THREADS];
+    const int tid = threadIdx.x;
     const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= p.R) return;
     const float ox = p.o[3 * (size_t)ray], oy = p.o[3 * (size_t)ray + 1], oz = p.o[3 * (size_t)ray + 2];
@@ -84,7 +91,7 @@ __global__ void __launch_bounds__(64) k_walk(const WalkParams p) {
     // ---- walk ----
     uint32_t c = btet, jin = bj, fin = (uint32_t)best, nfaces = 1, nrec = 0;
     float t_in = __uint_as_float((uint32_t)(best >> 32)), u_in = bu, v_in = bv;
-    bool generic = true, exact = false;
+    bool generic = true, exact = false, prev_small = false;
     p.keys[row] = best;
     for (;;) {
         const float4 *wp = reinterpret_cast<const float4 *>(p.walk + c);
@@ -92,27 +99,44 @@ __global__ void __launch_bounds__(64) k_walk(const WalkParams p) {
         const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(wp + 4));
         const uint4 vid = __ldg(reinterpret_cast<const uint4 *>(wp + 5));
         const uint32_t wind = __ldg(reinterpret_cast<const uint32_t *>(wp + 6));
-        const uint32_t fw[4] = {__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w), __float_as_uint(v3.w)};
-        if (nrec != 0 || true) {  // locate the entry face inside this tetrahedron (after the first step it is the shared face)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if ((fw[j] & TN_FACE_MASK) == fin) jin = (uint32_t)j;
+        // the next record is one of the neighbours: start fetching all of them while this tetrahedron is intersected
+        if (nb.x != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nb.x));
+        if (nb.y != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nb.y));
+        if (nb.z != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nb.z));
+        if (nb.w != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nb.w));
+        const uint32_t fw0 = __float_as_uint(v0.w), fw1 = __float_as_uint(v1.w), fw2 = __float_as_uint(v2.w), fw3 = __float_as_uint(v3.w);
+        // locate the entry face inside this tetrahedron (after the first step it is the face shared with the previous one)
+        jin = (fw0 & TN_FACE_MASK) == fin ? 0u : ((fw1 & TN_FACE_MASK) == fin ? 1u : ((fw2 & TN_FACE_MASK) == fin ? 2u : 3u));
+        {
+            const Sheared s0 = shear(rs, v0.x, v0.y, v0.z), s1 = shear(rs, v1.x, v1.y, v1.z), s2 = shear(rs, v2.x, v2.y, v2.z), s3 = shear(rs, v3.x, v3.y, v3.z);
+            ssm[0][tid] = s0.x; ssm[1][tid] = s0.y; ssm[2][tid] = s0.z; ssm[3][tid] = s1.x; ssm[4][tid] = s1.y; ssm[5][tid] = s1.z;
+            ssm[6][tid] = s2.x; ssm[7][tid] = s2.y; ssm[8][tid] = s2.z; ssm[9][tid] = s3.x; ssm[10][tid] = s3.y; ssm[11][tid] = s3.z;
         }
-        const Sheared s[4] = {shear(rs, v0.x, v0.y, v0.z), shear(rs, v1.x, v1.y, v1.z), shear(rs, v2.x, v2.y, v2.z), shear(rs, v3.x, v3.y, v3.z)};
         uint32_t hits = 0, jout = 0;
         float t_out = 0.f, u_out = 0.f, v_out = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if ((uint32_t)j == jin) continue;
             const uint32_t w = (wind >> (6 * j)) & 63u;
+            const uint32_t a = (w & 3u) * 3u, b = ((w >> 2) & 3u) * 3u, cc = ((w >> 4) & 3u) * 3u;
+            Sheared A, B, Cv;
+            A.x = ssm[a][tid]; A.y = ssm[a + 1][tid]; A.z = ssm[a + 2][tid];
+            B.x = ssm[b][tid]; B.y = ssm[b + 1][tid]; B.z = ssm[b + 2][tid];
+            Cv.x = ssm[cc][tid]; Cv.y = ssm[cc + 1][tid]; Cv.z = ssm[cc + 2][tid];
             float t, u, v;
-            if (tri_test(s[w & 3u], s[(w >> 2) & 3u], s[(w >> 4) & 3u], t, u, v)) { hits++; jout = (uint32_t)j; t_out = t; u_out = u; v_out = v; }
+            if (tri_test(A, B, Cv, t, u, v)) { hits++; jout = (uint32_t)j; t_out = t; u_out = u; v_out = v; }
         }
         if (hits != 1) { exact = true; break; }
-        const uint32_t fout = fw[jout] & TN_FACE_MASK;
-        if (t_out < t_in || fabsf(__fsub_rn(t_out, t_in)) < TN_EPS) generic = false;
-        if (generic) {
+        const uint32_t fout = sel4u(jout, fw0, fw1, fw2, fw3) & TN_FACE_MASK;
+        // An ISOLATED crossing shorter than eps (strictly increasing t, both neighbouring crossings >= eps) leaves the
+        // reference's dedupe phase without effect (optix_trace_rays.cu:124-159: the two faces share the sliver, nothing was
+        // marked before, the mark is cleared again) and its pairing phase just skips that record (:208).  Anything else
+        // within eps (ties, inversions, two short crossings in a row) goes to the literal implementation.
+        const bool small = fabsf(__fsub_rn(t_out, t_in)) < TN_EPS;
+        if (!(t_out > t_in) || (small && prev_small)) generic = false;
+        prev_small = small;
+        if (generic && !small) {
             // record (optix_trace_rays.cu:216-225 with combine_indices :39-75), expressed in local vertex indices
-            const uint32_t vv[4] = {vid.x, vid.y, vid.z, vid.w};
             const uint32_t wi = (wind >> (6 * jin)) & 63u, wo = (wind >> (6 * jout)) & 63u;
             const uint32_t ia[3] = {wi & 3u, (wi >> 2) & 3u, (wi >> 4) & 3u}, oa[3] = {wo & 3u, (wo >> 2) & 3u, (wo >> 4) & 3u};
             const float r2[3] = {__fsub_rn(__fsub_rn(1.0f, u_out), v_out), u_out, v_out};
@@ -124,23 +148,24 @@ __global__ void __launch_bounds__(64) k_walk(const WalkParams p) {
                     if (ia[q] == oa[i]) o2[q] = r2[i];
             const size_t g = row + nrec;
             p.cells[g] = c;
-            reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(vv[jin], vv[ia[0]], vv[ia[1]], vv[ia[2]]);
+            reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(sel4u(jin, vid.x, vid.y, vid.z, vid.w), sel4u(ia[0], vid.x, vid.y, vid.z, vid.w),
+                                                               sel4u(ia[1], vid.x, vid.y, vid.z, vid.w), sel4u(ia[2], vid.x, vid.y, vid.z, vid.w));
             float2 *bp = reinterpret_cast<float2 *>(p.bary + 6 * g);
             bp[0] = make_float2(__fsub_rn(__fsub_rn(1.0f, u_in), v_in), u_in);
             bp[1] = make_float2(v_in, o2[0]);
             bp[2] = make_float2(o2[1], o2[2]);
             reinterpret_cast<float2 *>(p.dist)[g] = make_float2(t_in, t_out);
+            nrec++;
         }
         p.keys[row + nfaces] = ((u64)__float_as_uint(t_out) << 32) | fout;
         nfaces++;
-        nrec++;
-        const uint32_t nbv[4] = {nb.x, nb.y, nb.z, nb.w};
-        const uint32_t next = nbv[jout];
+        const uint32_t next = sel4u(jout, nb.x, nb.y, nb.z, nb.w);
         if (next == TN_EMPTY || nfaces >= p.M - 1) break;  // left the mesh, or the M-1 nearest faces are in (optix_trace_rays.cu:312-315)
         c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out;
     }
     if (exact) {
         p.list[atomicAdd(p.list_count, 1u)] = ray;
+        atomicAdd(p.list_count + 1, 1u);  // diagnostics: rays that need the all-hits gather
         p.num[ray] = 0;
     } else if (!generic) {
         p.list[atomicAdd(p.list_count, 1u)] = ray | 0x80000000u;
@@ -173,7 +198,7 @@ int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32
     p.o = o; p.d = d; p.R = R; p.M = M; p.num = num; p.cells = cells; p.bary = bary; p.dist = dist; p.verts = verts;
     p.walk = h->mesh.walk; p.hull_nodes = h->mesh.hull_nodes; p.hull_leaves = h->mesh.hull_leaves; p.hull_tet = h->mesh.hull_tet;
     p.hlv = h->mesh.hull_lv; p.absmax = h->mesh.absmax; p.keys = keys; p.list = list; p.list_count = list_count;
-    k_walk<<<(R + 63) / 64, 64, 0, s>>>(p);
+    k_walk<<<(R + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(p);
     h->launches += 1;
     TN_CUDA(cudaGetLastError());
     return TN_OK;

@@ -35,6 +35,7 @@ _lib.tn_find_visited_cells.argtypes = [_vp, _u32, _u32, _u32] + [_vp] * 11
 _lib.tn_interpolate_values.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]
 _lib.tn_interpolate_values_backward.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]
 _lib.tn_debug_trace_stats.argtypes = [_vp, C.POINTER(_u32)]
+_lib.tn_set_walk_min_rays.argtypes = [_vp, _u32]
 _lib.tn_launch_count.restype = C.c_uint64
 _lib.tn_launch_count.argtypes = [_vp]
 
@@ -134,6 +135,10 @@ class TetrahedraTracer:
         """Stream sync + deferred device-side error check (the reference syncs on every call,
         src/tetrahedra_tracer.cpp:173-174; here it is explicit)."""
         _check(_lib.tn_synchronize(self._h, _stream(self._device)))
+
+    def set_walk_min_rays(self, n: int) -> None:
+        """batches of >= n rays use the adjacency-walk implementation of trace_rays (0 = always, 2**32-1 = never)"""
+        _check(_lib.tn_set_walk_min_rays(self._h, int(n)))
 
     def trace_stats(self):
         """(walkable mesh?, rays of the last trace_rays that took the exact stage) -- test/diagnostic hook"""
