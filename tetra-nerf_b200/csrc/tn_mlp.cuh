@@ -103,15 +103,19 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
                                                const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc) {
     using namespace tc;
     float2 dsum = make_float2(0.f, 0.f), c0 = dsum, c1 = dsum, c2 = dsum;
+    // 4 chunks of 16 accumulator columns (small register footprint); the TMEM load of chunk ch+1 is in flight while
+    // chunk ch is processed
+    uint32_t rbuf[2][16];
+    tmem_ld16(d_t + h * 64u, rbuf[0]);
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-        const uint32_t col0 = h * 64u + ch * 32u;
-        uint32_t r[32];
-        tmem_ld32(d_t + col0, r);
+    for (int ch = 0; ch < 4; ++ch) {
+        const uint32_t col0 = h * 64u + ch * 16u;
         tmem_ld_wait();
-        uint32_t ph[16], pl[16];
+        if (ch + 1 < 4) tmem_ld16(d_t + col0 + 16u, rbuf[(ch + 1) & 1]);
+        const uint32_t *r = rbuf[ch & 1];
+        uint32_t ph[8], pl[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const float2 b = *reinterpret_cast<const float2 *>(bias128 + col0 + 2 * i);
             float2 x = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b);
             x.x = fmaxf(x.x, 0.f);
@@ -125,8 +129,8 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
             }
         }
         if (KIND == 0 || KIND == 1) {
-            tmem_st16(ahi + (col0 >> 1), ph);
-            tmem_st16(alo + (col0 >> 1), pl);
+            tmem_st8(ahi + (col0 >> 1), ph);
+            tmem_st8(alo + (col0 >> 1), pl);
         }
     }
     if (KIND == 1 || KIND == 2) acc.x = dsum.x + dsum.y;
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
 #pragma unroll
             for (int l = 0; l < L; ++l) {
                 tl_mark(p.timeline, lane, warp, 7, it, l);  // ev 7: start waiting for D
-                mbar_wait_backoff(&d_ready[slot], dpar, 64);
+                mbar_wait_backoff(&d_ready[slot], dpar, 32);
                 dpar ^= 1u;
                 fence_after_sync();
                 tl_mark(p.timeline, lane, warp, 8, it, l);  // ev 8: D ready seen
