@@ -203,8 +203,11 @@ __device__ __forceinline__ void match_sample(float d, uint32_t n, const float *t
     }
 }
 
-// shared memory per warp: 7 arrays (t_in t_out pm aux e x y) of A = max(M, Smax) + 2 floats each
-__host__ __device__ __forceinline__ size_t sample_arr(uint32_t M, uint32_t Smax) { return (size_t)(M > Smax ? M : Smax) + 2; }
+// shared memory per warp: 3 segment arrays (t_in t_out pm) of M+2 floats and 4 bin/weight arrays (aux e x y) of
+// max(Smax, M when the biased sampler needs cum[M+1]) + 2 floats
+__host__ __device__ __forceinline__ size_t seg_arr(uint32_t M) { return (size_t)M + 2; }
+__host__ __device__ __forceinline__ size_t bin_arr(uint32_t M, uint32_t Smax, uint32_t biased) { return (size_t)((biased && M > Smax) ? M : Smax) + 2; }
+__host__ __device__ __forceinline__ size_t sample_floats(uint32_t M, uint32_t Smax, uint32_t biased) { return 3 * seg_arr(M) + 4 * bin_arr(M, Smax, biased); }
 
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const SampleParams p) {
     extern __shared__ float sm[];
@@ -212,9 +215,9 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const Sampl
     const uint32_t ray = blockIdx.x * SAMPLE_WARPS + warp;
     if (ray >= p.R) return;
     const uint32_t M = p.M, S = p.Sc;
-    const size_t A = sample_arr(M, max(p.Sc, p.S2));
-    float *t_in = sm + (size_t)warp * 7 * A;
-    float *t_out = t_in + A, *pm = t_out + A, *cum = pm + A, *e = cum + A;
+    const size_t A = seg_arr(M), B = bin_arr(M, max(p.Sc, p.S2), 1);
+    float *t_in = sm + (size_t)warp * (3 * A + 4 * B);
+    float *t_out = t_in + A, *pm = t_out + A, *cum = pm + A, *e = cum + B;
     const uint32_t n = p.num[ray];
     if (n == 0) {  // model.py:640-650 : background colour, accumulation 0, depth = collider far plane
         if (lane == 0) {
@@ -288,9 +291,9 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_fine(const SampleP
     const uint32_t slot = blockIdx.x * SAMPLE_WARPS + warp;
     if (slot >= *p.n_active) return;
     const uint32_t M = p.M, S = p.Sc, S2 = p.S2, nb = p.Sf + 1;
-    const size_t A = sample_arr(M, max(p.Sc, p.S2));
-    float *t_in = sm + (size_t)warp * 7 * A;
-    float *t_out = t_in + A, *pm = t_out + A, *cdf = pm + A, *e = cdf + A, *x = e + A, *y = x + A;
+    const size_t A = seg_arr(M), B = bin_arr(M, max(p.Sc, p.S2), 0);
+    float *t_in = sm + (size_t)warp * (3 * A + 4 * B);
+    float *t_out = t_in + A, *pm = t_out + A, *cdf = pm + A, *e = cdf + B, *x = e + B, *y = x + B;
     const uint32_t ray = p.ray_list[slot];
     const uint32_t n = p.num[ray];
     const size_t row = (size_t)ray * M;
@@ -520,10 +523,11 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     p.rgb = d_rgb; p.acc = d_acc; p.depth = d_depth; p.mask = d_mask;
     p.far_plane = cfg->far_plane; p.bg0 = cfg->background[0]; p.bg1 = cfg->background[1]; p.bg2 = cfg->background[2];
     const uint32_t Smax = std::max(Sc, S2);
-    const size_t smem_s = SAMPLE_WARPS * sizeof(float) * 7 * sample_arr(M, Smax);
+    const size_t smem_sc = SAMPLE_WARPS * sizeof(float) * sample_floats(M, Smax, 1);  // coarse: cum[] has M+1 entries
+    const size_t smem_sf = SAMPLE_WARPS * sizeof(float) * sample_floats(M, Smax, 0);
     const size_t smem_c = SAMPLE_WARPS * sizeof(float) * 2 * ((size_t)S2 + 2);
-    TN_CUDA(cudaFuncSetAttribute(k_sample_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-    TN_CUDA(cudaFuncSetAttribute(k_sample_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    TN_CUDA(cudaFuncSetAttribute(k_sample_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
+    TN_CUDA(cudaFuncSetAttribute(k_sample_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sf));
     TN_CUDA(cudaFuncSetAttribute(k_composite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     TN_CUDA(cudaFuncSetAttribute(k_mlp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
     TN_CUDA(cudaFuncSetAttribute(k_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
@@ -531,7 +535,7 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const uint32_t gridR = (R + SAMPLE_WARPS - 1) / SAMPLE_WARPS;
 
-    k_sample_coarse<<<gridR, SAMPLE_WARPS * 32, smem_s, s>>>(p);
+    k_sample_coarse<<<gridR, SAMPLE_WARPS * 32, smem_sc, s>>>(p);
     TN_EV(2);
     MlpParams mc{};
     mc.n_active = r->n_active; mc.S = Sc; mc.vi = r->vi_c; mc.bary = r->bary_c; mc.fshadow = r->fshadow; mc.wimg = r->wimg;
@@ -539,7 +543,7 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     const uint32_t tiles_c = (uint32_t)(((uint64_t)R * Sc + 127) / 128), tiles_f = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
     k_mlp<false><<<std::min<uint32_t>(tiles_c, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mc);
     TN_EV(3);
-    k_sample_fine<<<gridR, SAMPLE_WARPS * 32, smem_s, s>>>(p);
+    k_sample_fine<<<gridR, SAMPLE_WARPS * 32, smem_sf, s>>>(p);
     TN_EV(4);
     MlpParams mf = mc;
     mf.S = S2; mf.vi = r->vi_f; mf.bary = r->bary_f; mf.dirbias = r->dirbias; mf.out = r->out_f;
