@@ -130,7 +130,13 @@ struct RaySetup {
     bool valid;
 };
 
-__device__ __forceinline__ float sel3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
+// branch-free 3-way select (k is a per-ray constant; nested ternaries on floats tend to become divergent branches)
+__device__ __forceinline__ float sel3(int k, float x, float y, float z) {
+    float r;
+    asm("{\n\t.reg .pred p1, p2;\n\tsetp.eq.s32 p1, %4, 1;\n\tsetp.eq.s32 p2, %4, 2;\n\tselp.f32 %0, %2, %1, p1;\n\tselp.f32 %0, %3, %0, p2;\n\t}"
+        : "=&f"(r) : "f"(x), "f"(y), "f"(z), "r"(k));
+    return r;
+}
 
 __device__ __forceinline__ RaySetup ray_setup(float ox, float oy, float oz, float dx, float dy, float dz) {
     RaySetup r;

@@ -324,26 +324,40 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 7) k_trace(const TraceParams
             // ---------------- 3. face pairing ----------------
             uint2 *tts = reinterpret_cast<uint2 *>(stack);
             uint16_t *emit = reinterpret_cast<uint16_t *>(leafq);
-            bool generic = true;
             if (nh >= 2) {
                 for (uint32_t j = lane; j < nh; j += 32) tts[j] = __ldg(p.tt + key_face(hits[j]));
                 __syncwarp();
+                // Parallel pairing whenever the literal algorithm reduces to "pair consecutive hits, skip crossings shorter
+                // than eps": every consecutive pair shares a tetrahedron, and a crossing shorter than eps is ISOLATED
+                // (strictly increasing t, both neighbouring crossings >= eps) -- then the dedupe phase marks and unmarks
+                // without deleting (optix_trace_rays.cu:124-159) and the pairing phase skips that record (:208).
                 bool ok = true;
                 for (uint32_t j = lane; j + 1 < nh; j += 32) {
                     uint32_t cell;
-                    if (fabsf(__fsub_rn(key_t(hits[j + 1]), key_t(hits[j]))) < TN_EPS) ok = false;
+                    const float tj = key_t(hits[j]), tn = key_t(hits[j + 1]);
                     if (!common_tet(tts[j], tts[j + 1], cell)) ok = false;
+                    if (fabsf(__fsub_rn(tn, tj)) < TN_EPS) {
+                        if (!(tn > tj)) ok = false;
+                        if (j > 0 && fabsf(__fsub_rn(tj, key_t(hits[j - 1]))) < TN_EPS) ok = false;
+                        if (j + 2 < nh && fabsf(__fsub_rn(key_t(hits[j + 2]), tn)) < TN_EPS) ok = false;
+                    }
                 }
-                generic = __all_sync(FULL, ok);
-                if (generic) jc = nh - 1;
-                else {
+                if (__all_sync(FULL, ok)) {
+                    for (uint32_t base = 0; base + 1 < nh; base += 32) {  // compact the emitted pair indices
+                        const uint32_t j = base + lane;
+                        const bool em = j + 1 < nh && !(fabsf(__fsub_rn(key_t(hits[j + 1]), key_t(hits[j]))) < TN_EPS);
+                        const uint32_t mask = __ballot_sync(FULL, em);
+                        if (em) emit[jc + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)j;
+                        jc += __popc(mask);
+                    }
+                } else {
                     if (lane == 0) jc = post_process_serial(hits, tts, nh, emit);
                     jc = __shfl_sync(FULL, jc, 0);
                 }
                 __syncwarp();
             }
             for (uint32_t r = lane; r < jc; r += 32) {
-                const uint32_t j = generic ? r : (uint32_t)emit[r];
+                const uint32_t j = (uint32_t)emit[r];
                 const uint32_t f0 = key_face(hits[j]), f1 = key_face(hits[j + 1]);
                 const uint4 tr0 = __ldg(p.tri + f0), tr1 = __ldg(p.tri + f1);
                 float t0, u0, v0, t1, u1, v1;
