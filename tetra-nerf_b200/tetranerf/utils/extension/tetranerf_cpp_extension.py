@@ -174,6 +174,16 @@ class TetrahedraTracer:
             "hit_distances": dist,
         }
 
+    def trace_rays_into(self, ray_origins, ray_directions, max_ray_triangles: int, out: dict, dense: bool = False):
+        """trace_rays into caller-provided tensors (same keys/shapes as trace_rays); dense=False skips the tail fill
+        (entries >= num_visited_cells are left untouched) -- the form the fused renderer uses; for benchmarking."""
+        M = int(max_ray_triangles)
+        R = ray_origins.numel() // 3
+        _check(_lib.tn_trace_rays(self._h, ray_origins.data_ptr(), ray_directions.data_ptr(), R, M, out["num_visited_cells"].data_ptr(),
+                                  out["visited_cells"].data_ptr(), out["barycentric_coordinates"].data_ptr(), out["hit_distances"].data_ptr(),
+                                  out["vertex_indices"].data_ptr(), int(dense), _stream(self._device)))
+        return out
+
     # ---- trace_rays_triangles (py_binding.cpp:78-113) --------------------------------------------
     def trace_rays_triangles(self, ray_origins: torch.Tensor, ray_directions: torch.Tensor, max_ray_triangles: int):
         M = int(max_ray_triangles)
