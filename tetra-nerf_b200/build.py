@@ -1,6 +1,7 @@
 """Builds csrc/libtetranerf_b200.so for sm_100a with nvcc (in-tree, so that it travels with gpurun)."""
 from __future__ import annotations
 
+import os
 import subprocess
 from pathlib import Path
 
@@ -27,7 +28,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in SOURCES:  # compile translation units in parallel, then link
         obj = CSRC / (src[:-3] + ".o")
         objs.append(str(obj))
-        cmd = ["nvcc", *FLAGS[:-1], "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = ["nvcc", *FLAGS[:-1], *os.environ.get("TN_EXTRA_NVCC_FLAGS", "").split(), "-c", str(CSRC / src), "-o", str(obj)]  # extra flags: experiments only
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

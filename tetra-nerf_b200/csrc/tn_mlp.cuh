@@ -6,20 +6,22 @@
 //   (Linear+Sigmoid, :454)]                                               (call sites model.py:569-621)
 // which the reference runs as ~10 torch kernels with [R*S,128] fp32 activations round-tripping HBM.
 //
-// One persistent CTA per SM, 18 warps:
-//   warp 17     : issues every tcgen05.mma (one elected lane), strictly alternating between the two slots; it has the
-//                 highest warp id because the SM's warp arbiter is highest-id-first and the issuer must never starve
-//   warp 16     : TMEM allocation, TMA bulk staging of the resident weight image, and (FINE) the
-//                 producer of the 2-stage TMA ring that streams the 4th layer's weights
-//   warps 0..15 : two "slots" of 8 warps.  A slot owns one 128-sample tile at a time; warp (q,h) of a
-//                 slot owns sample rows 32q..32q+31 (its TMEM lane quarter, q = warp_id % 4) and the
-//                 column half h.  It gathers the four vertex rows of its samples from the [V,64] field
-//                 shadow with coalesced 128-byte reads, forms the barycentric interpolation with the
-//                 reference's FMA order, splits it into bf16 hi/lo and writes it into TMEM as the A
-//                 operand; then for each layer it waits for the accumulator, applies bias + ReLU to its
-//                 64 columns, splits again and writes the next A operand back into TMEM (activations
-//                 never touch shared or global memory).  The two slots run half a tile apart, so one
-//                 slot's epilogue overlaps the other slot's MMAs.
+// One persistent CTA per SM, 24 warps in six warpgroups with per-role register budgets (setmaxnreg):
+//   warps 0..15  : epilogue workers, two "slots" of 8 warps.  A slot owns one 128-sample tile at a time; warp (q,h)
+//                  of a slot owns sample rows 32q..32q+31 (its TMEM lane quarter, q = warp_id % 4) and the column
+//                  half h.  For each layer it waits for the accumulator, applies bias + ReLU to its 64 columns, splits
+//                  the result into bf16 hi/lo and writes the next A operand back into TMEM (activations never touch
+//                  shared or global memory); the last layer's epilogue also forms the head dot products.
+//   warp 16      : TMEM allocation, TMA bulk staging of the resident weight image, and (FINE) the producer of the
+//                  2-stage TMA ring that streams the 4th layer's weights in 16 KB (128 output rows x 64 K) chunks
+//   warp 17      : issues every tcgen05.mma (one elected lane), strictly alternating between the two slots, which run
+//                  half a tile apart: one slot's epilogue overlaps the other slot's MMAs
+//   warps 20..23 : gather warps.  They run AHEAD of the slots: tile after tile they fetch the four vertex rows of
+//                  every sample from the [V,64] field shadow (16-byte loads, 16 in flight per lane), form the
+//                  barycentric interpolation with the reference's FMA order, split it into bf16 hi/lo and store it
+//                  as the layer-0 A operand in shared memory (K-major, 128-byte swizzle), so the L2 latency of the
+//                  gather hides under the MMAs and epilogues of the previous tiles.  Layer 0 is an SS MMA (A and B
+//                  from shared memory), layers 1.. are TS MMAs (A from TMEM).
 // Products are "bf16x3": a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation in TMEM
 // (measured 5e-6 relative on B200, tests/test_gpu_mlp.py) -- the reference computes in fp32 and the
 // parity bar is 1e-4 absolute on colour/density, which single-pass bf16/tf32 cannot hold.
@@ -28,21 +30,31 @@
 #include "tn_common.cuh"
 #include "tn_tc.cuh"
 
+#ifndef TN_MLP_STATS
+#define TN_MLP_STATS 0   // 1: the gather warps also accumulate busy / wait cycles into the debug timeline (costs registers)
+#endif
+#ifndef TN_MLP_GATHER_ON
+#define TN_MLP_GATHER_ON true
+#endif
 namespace tn {
 
-constexpr uint32_t MLP_THREADS = 576;
-constexpr uint32_t MLP_TL_CAP = 960;  // debug timeline records buffered in shared memory
-constexpr uint32_t MLP_W_RESIDENT = 163840;               // L1 32K + L2 64K + L3 64K
-constexpr uint32_t MLP_OFF_RING = MLP_W_RESIDENT;          // 2 x 16K
-constexpr uint32_t MLP_OFF_STAGE = MLP_OFF_RING + 32768;   // 16 warps x 4 rows x 36 floats
-constexpr uint32_t MLP_STAGE_STRIDE = 36;                  // floats per staged sample row (32 features + pad)
-constexpr uint32_t MLP_OFF_BIAS = MLP_OFF_STAGE + 16 * 4 * MLP_STAGE_STRIDE * 4;  // 3 x 128 floats (b1,b2,b3)
-constexpr uint32_t MLP_OFF_HEAD = MLP_OFF_BIAS + 3 * 128 * 4;                     // wd[128] wc[3][128] bd bc[3] (+pad)
-constexpr uint32_t MLP_OFF_DIRB = MLP_OFF_HEAD + 520 * 4;                         // 2 slots x 4 rays x 128 floats
-constexpr uint32_t MLP_OFF_RED = MLP_OFF_DIRB + 2 * 4 * 128 * 4;                  // 2 slots x 128 rows x float4 (head partials)
-constexpr uint32_t MLP_OFF_BARS = MLP_OFF_RED + 2 * 128 * 16;
-constexpr uint32_t MLP_OFF_TL = MLP_OFF_BARS + 128;  // debug timeline: counter + MLP_TL_CAP records
-constexpr uint32_t MLP_SMEM_BYTES = MLP_OFF_TL + 8 * (MLP_TL_CAP + 1);
+constexpr uint32_t MLP_THREADS = 768;
+constexpr uint32_t MLP_GATHER_WARP0 = 20, MLP_GATHER_WARPS = 4;
+// setmaxnreg only moves registers inside the CTA's launch allocation (768 threads x 80): 512*88 + 128*40 + 128*88 = 61440
+constexpr uint32_t MLP_REGS_WORKER = 88, MLP_REGS_CTRL = 40, MLP_REGS_GATHER = 88;
+static_assert(512 * MLP_REGS_WORKER + 128 * MLP_REGS_CTRL + 128 * MLP_REGS_GATHER <= MLP_THREADS * 80, "register budget exceeds the launch allocation: setmaxnreg.inc would block forever");
+constexpr uint32_t MLP_TL_CAP = 96;                        // debug timeline records buffered in shared memory
+constexpr uint32_t MLP_W_RESIDENT = 163840;                // L1 32K + L2 64K + L3 64K
+constexpr uint32_t MLP_RING_STAGES = 2, MLP_RING_CHUNK = 16384;
+constexpr uint32_t MLP_OFF_RING = MLP_W_RESIDENT;                                // 2 x 16K
+constexpr uint32_t MLP_OFF_A0 = MLP_OFF_RING + MLP_RING_STAGES * MLP_RING_CHUNK; // layer-0 A operand: hi 16K | lo 16K
+constexpr uint32_t MLP_OFF_HEAD = MLP_OFF_A0 + 32768;                            // wd[128] wc[3][128] bd bc[3] (+pad)
+constexpr uint32_t MLP_OFF_BARS = MLP_OFF_HEAD + 520 * 4;
+constexpr uint32_t MLP_OFF_TL = MLP_OFF_BARS + 144;  // debug timeline: counter, enable flag, MLP_TL_CAP records
+// (the hidden-layer biases are read through L1 and the head partial sums are exchanged through TMEM: with 160 KB of
+//  resident weights, the 32 KB ring and the 32 KB layer-0 operand there is no shared memory left for them)
+constexpr uint32_t MLP_SMEM_BYTES = MLP_OFF_TL + 8 * (MLP_TL_CAP + 2);
+static_assert(MLP_OFF_A0 % 1024 == 0 && MLP_OFF_RING % 1024 == 0, "swizzled operands need 1024-byte alignment");
 static_assert(MLP_SMEM_BYTES <= 232448, "k_mlp shared memory exceeds 227 KB");
 
 struct MlpParams {
@@ -56,6 +68,7 @@ struct MlpParams {
     const float *head;         // wd[128], wc[3][128], bd, bc[3]
     const float *dirbias;      // FINE: [n_active,128]  = b4 + W4[:, :27] . enc(dir)
     float *out;                // COARSE: density [rows] ; FINE: (sigma,r,g,b) [rows,4]
+    uint32_t *tile_ctr;        // device counter (zeroed before the launch): dynamic tile scheduler
     unsigned long long *timeline;  // debug: [0] = count, then (tag << 40 | clock) records of CTA 0; nullptr in production
 };
 
@@ -116,7 +129,7 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
         uint32_t ph[8], pl[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float2 b = *reinterpret_cast<const float2 *>(bias128 + col0 + 2 * i);
+            const float2 b = __ldg(reinterpret_cast<const float2 *>(bias128 + col0 + 2 * i));  // global, L1-resident
             float2 x = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b);
             x.x = fmaxf(x.x, 0.f);
             x.y = fmaxf(x.y, 0.f);
@@ -139,11 +152,143 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
 
 extern __shared__ __align__(1024) uint8_t tn_mlp_smem[];
 __device__ __forceinline__ void tl_mark(unsigned long long *buf, int lane, uint32_t warp, uint32_t ev, uint32_t it, uint32_t layer) {
-    if (buf != nullptr && blockIdx.x == 0 && lane == 0) {
-        unsigned long long *tl = reinterpret_cast<unsigned long long *>(tn_mlp_smem + MLP_OFF_TL);
-        const unsigned long long i = atomicAdd(tl, 1ull);
-        if (i < MLP_TL_CAP) tl[1 + i] = ((unsigned long long)(warp | (ev << 5) | ((it & 255u) << 9) | (layer << 17)) << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+    // records warps 0, 8 (one worker per slot), 17 (issuer), 20 (gather) of CTA 0 once the enable flag is set (steady state)
+    if (buf != nullptr && blockIdx.x == 0 && lane == 0 && ((0x00120101u >> warp) & 1u)) {
+        volatile unsigned long long *tl = reinterpret_cast<volatile unsigned long long *>(tn_mlp_smem + MLP_OFF_TL);
+        if (tl[1] != 0ull) {
+            const unsigned long long i = atomicAdd(const_cast<unsigned long long *>(tl), 1ull);
+            if (i < MLP_TL_CAP) tl[2 + i] = ((unsigned long long)(warp | (ev << 5) | ((it & 255u) << 9) | (layer << 17)) << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+        }
     }
+}
+
+// 16-byte read-only load that does not allocate in L1 (the gathered field rows stream through; L1 is left to the biases)
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <uint32_t N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <uint32_t N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// state of the MMA issuer: scalars and 32-bit shared-memory addresses only (it runs with a 40-register budget and nothing
+// here may end up in local memory); barrier k of the kernel's barrier block is at bars + 8 k
+struct MlpIssue {
+    uint32_t tbase, bars;
+    uint32_t dw, dr, da0;  // low descriptor words (address >> 4) of the resident image, the layer-4 ring and the layer-0 A operand
+    uint32_t rst, rpar;    // ring stage / parity
+    uint32_t nseq, done;   // sequence number of the CTA's next tile; set once the tile scheduler has run dry
+};
+constexpr uint32_t MLP_BAR_A_READY = 0, MLP_BAR_D_READY = 2, MLP_BAR_W = 4, MLP_BAR_RING_FULL = 5, MLP_BAR_RING_EMPTY = 7, MLP_BAR_A0_FULL = 9,
+                   MLP_BAR_A0_EMPTY = 11;
+constexpr uint32_t MLP_TILE_IDS_OFF = 112;        // byte offset of tile_ids[8] inside the barrier block (after 13 barriers + tmem ptr + stop flag)
+constexpr uint32_t MLP_NO_TILE = 0xFFFFFFFFu;     // sentinel: the scheduler has run dry
+
+// 12 MMAs of one 64-wide K block KB with A in TMEM: (A_hi,W_hi) (A_lo,W_hi) (A_hi,W_lo).  a = TMEM address of A_hi
+// (A_lo is 64 columns further); WH / WL = low-descriptor-word offsets of the hi / lo weight blocks in the resident image
+template <bool FIRST, uint32_t KB, uint32_t WH, uint32_t WL>
+__device__ __forceinline__ void kblock_ts(uint32_t d_t, uint32_t a, uint32_t dw, uint32_t idesc) {
+    using namespace tc;
+    mma_ts_o<!FIRST, KB * 32u + 0u, WH + 0u>(d_t, a, dw, idesc);
+    mma_ts_o<true, KB * 32u + 8u, WH + 2u>(d_t, a, dw, idesc);
+    mma_ts_o<true, KB * 32u + 16u, WH + 4u>(d_t, a, dw, idesc);
+    mma_ts_o<true, KB * 32u + 24u, WH + 6u>(d_t, a, dw, idesc);
+    mma_ts_o<true, 64u + KB * 32u + 0u, WH + 0u>(d_t, a, dw, idesc);
+    mma_ts_o<true, 64u + KB * 32u + 8u, WH + 2u>(d_t, a, dw, idesc);
+    mma_ts_o<true, 64u + KB * 32u + 16u, WH + 4u>(d_t, a, dw, idesc);
+    mma_ts_o<true, 64u + KB * 32u + 24u, WH + 6u>(d_t, a, dw, idesc);
+    mma_ts_o<true, KB * 32u + 0u, WL + 0u>(d_t, a, dw, idesc);
+    mma_ts_o<true, KB * 32u + 8u, WL + 2u>(d_t, a, dw, idesc);
+    mma_ts_o<true, KB * 32u + 16u, WL + 4u>(d_t, a, dw, idesc);
+    mma_ts_o<true, KB * 32u + 24u, WL + 6u>(d_t, a, dw, idesc);
+}
+
+// one ring chunk of layer 4: BLK 0: hi kb0, 1: lo kb0, 2: hi kb1, 3: lo kb1 (128 output rows x 64 K); hi blocks take A_hi and A_lo
+template <int BLK>
+__device__ __forceinline__ void ring_chunk(uint32_t d_t, uint32_t a, uint32_t b, uint32_t idesc) {
+    using namespace tc;
+    constexpr uint32_t KB = (uint32_t)(BLK >> 1) * 32u;
+    mma_ts_o<(BLK != 0), KB + 0u, 0u>(d_t, a, b, idesc);
+    mma_ts_o<true, KB + 8u, 2u>(d_t, a, b, idesc);
+    mma_ts_o<true, KB + 16u, 4u>(d_t, a, b, idesc);
+    mma_ts_o<true, KB + 24u, 6u>(d_t, a, b, idesc);
+    if ((BLK & 1) == 0) {
+        mma_ts_o<true, 64u + KB + 0u, 0u>(d_t, a, b, idesc);
+        mma_ts_o<true, 64u + KB + 8u, 2u>(d_t, a, b, idesc);
+        mma_ts_o<true, 64u + KB + 16u, 4u>(d_t, a, b, idesc);
+        mma_ts_o<true, 64u + KB + 24u, 6u>(d_t, a, b, idesc);
+    }
+}
+
+// one layer of one slot; returns false when the slot has no further tile (its workers have been released)
+template <bool FINE, int SLOT>
+__device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &layer, const MlpParams &p) {
+    using namespace tc;
+    constexpr uint32_t L = FINE ? 4 : 3;
+    constexpr uint32_t NBUF = FINE ? 1 : 2;
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    mbar_wait_backoff_a(s.bars + 8u * (MLP_BAR_A_READY + SLOT), par, 32);
+    par ^= 1u;
+    const uint32_t l = layer;
+    layer = l + 1u == L ? 0u : l + 1u;
+    const uint32_t d_t = s.tbase + 256u * SLOT, a = d_t + 128u;
+    if (l == 0) {
+        // layer 0 of the CTA's next tile (sequence number nseq): A = interpolated features staged in shared memory by the
+        // gather warps (hi block, lo block 16 KB further); resident image: L1 hi at 0, lo at 16 KB
+        uint32_t tile = MLP_NO_TILE;
+        const uint32_t b = NBUF == 2 ? (s.nseq & 1u) : 0u;
+        if (!s.done) {
+            mbar_wait_backoff_a(s.bars + 8u * (MLP_BAR_A0_FULL + b), (s.nseq / NBUF) & 1u, 32);
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tile) : "r"(s.bars + MLP_TILE_IDS_OFF + 4u * (s.nseq & 7u)) : "memory");
+            s.nseq++;
+        }
+        if (tile == MLP_NO_TILE) {  // out of tiles: release the slot's workers (they read the same sentinel) and retire the slot
+            s.done = 1u;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s.bars + 8u * (MLP_BAR_D_READY + SLOT)) : "memory");
+            return false;
+        }
+        fence_after_sync();
+        tl_mark(p.timeline, 0, 17, 1 + SLOT, 0, l);
+        const uint32_t da = b ? s.dr : s.da0;  // COARSE: the second operand buffer lives in the (unused) ring area
+        mma_ss_o<false, 0u, 0u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 2u, 2u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 4u, 4u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 6u, 6u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 1024u + 0u, 0u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 1024u + 2u, 2u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 1024u + 4u, 4u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 1024u + 6u, 6u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 0u, 1024u + 0u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 2u, 1024u + 2u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 4u, 1024u + 4u>(d_t, da, s.dw, idesc);
+        mma_ss_o<true, 6u, 1024u + 6u>(d_t, da, s.dw, idesc);
+        mma_commit_a(s.bars + 8u * (MLP_BAR_A0_EMPTY + b));
+    } else {
+        fence_after_sync();
+        tl_mark(p.timeline, 0, 17, 1 + SLOT, 0, l);
+        if (l == 1) {
+            kblock_ts<true, 0u, 2048u, 3072u>(d_t, a, s.dw, idesc);
+            kblock_ts<false, 1u, 4096u, 5120u>(d_t, a, s.dw, idesc);
+        } else if (l == 2) {
+            kblock_ts<true, 0u, 6144u, 7168u>(d_t, a, s.dw, idesc);
+            kblock_ts<false, 1u, 8192u, 9216u>(d_t, a, s.dw, idesc);
+        } else {
+            // layer 4: the chunks hi(kb0) lo(kb0) hi(kb1) lo(kb1) stream through the ring
+#define TN_RING_CHUNK(J)                                                                              \
+    {                                                                                                 \
+        mbar_wait_a(s.bars + 8u * (MLP_BAR_RING_FULL + s.rst), s.rpar);                               \
+        ring_chunk<(J)>(d_t, a, s.dr + s.rst * (MLP_RING_CHUNK >> 4), idesc);                         \
+        mma_commit_a(s.bars + 8u * (MLP_BAR_RING_EMPTY + s.rst));                                     \
+        if (++s.rst == MLP_RING_STAGES) { s.rst = 0; s.rpar ^= 1u; }                                  \
+    }
+            TN_RING_CHUNK(0) TN_RING_CHUNK(1) TN_RING_CHUNK(2) TN_RING_CHUNK(3)
+#undef TN_RING_CHUNK
+        }
+    }
+    mma_commit_a(s.bars + 8u * (MLP_BAR_D_READY + SLOT));
+    tl_mark(p.timeline, 0, 17, 3 + SLOT, 0, l);
+    return true;
 }
 
 template <bool FINE>
@@ -152,283 +297,321 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
     uint8_t *smem = tn_mlp_smem;
     uint8_t *w_s = smem;
     uint8_t *ring_s = smem + MLP_OFF_RING;
-    float *bias_s = reinterpret_cast<float *>(smem + MLP_OFF_BIAS);
     float *head_s = reinterpret_cast<float *>(smem + MLP_OFF_HEAD);
-    float *dirb_s = reinterpret_cast<float *>(smem + MLP_OFF_DIRB);
-    float4 *red_s = reinterpret_cast<float4 *>(smem + MLP_OFF_RED);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + MLP_OFF_BARS);
-    uint64_t *a_ready = bars;          // [2] count 8 (one arrive per slot warp)
-    uint64_t *d_ready = bars + 2;      // [2] count 1 (tcgen05.commit)
-    uint64_t *w_bar = bars + 4;        // resident weights landed
-    uint64_t *ring_full = bars + 5;    // [2]
-    uint64_t *ring_empty = bars + 7;   // [2]
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 10);
+    uint64_t *a_ready = bars + MLP_BAR_A_READY;        // [2] count 8: the slot's warps are done with D / have written the next A
+    uint64_t *d_ready = bars + MLP_BAR_D_READY;        // [2] count 1 (tcgen05.commit; plain arrive when the slot is retired)
+    uint64_t *w_bar = bars + MLP_BAR_W;                // resident weights landed
+    uint64_t *ring_full = bars + MLP_BAR_RING_FULL;    // [2]
+    uint64_t *ring_empty = bars + MLP_BAR_RING_EMPTY;  // [2]
+    uint64_t *a0_full = bars + MLP_BAR_A0_FULL;        // [2] count 4: every gather warp has stored its rows of the layer-0 operand
+    uint64_t *a0_empty = bars + MLP_BAR_A0_EMPTY;      // [2] count 1 (tcgen05.commit after the layer-0 MMAs)
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 13);
+    volatile uint32_t *stop_flag = tmem_ptr + 1;       // set by the issuer when both slots are retired (stops the ring producer)
+    volatile uint32_t *tile_ids = reinterpret_cast<volatile uint32_t *>(smem + MLP_OFF_BARS + MLP_TILE_IDS_OFF);  // [8] tile of sequence number n at n & 7
 
     constexpr int L = FINE ? 4 : 3;
+    constexpr uint32_t NBUF = FINE ? 1 : 2;  // layer-0 operand buffers (COARSE has the ring area to spare)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_active = *p.n_active;
     const uint64_t total_rows = (uint64_t)n_active * p.S;
     const uint32_t ntiles = (uint32_t)((total_rows + 127) / 128);
-    const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // Tiles are handed out dynamically (the SMs do not run at the same speed: L2 distance shows up in every latency-bound
+    // phase): a CTA's first tile is blockIdx.x, the following ones come from a global counter.
+    const bool has_work = blockIdx.x < ntiles;
 
     if (warp == 16) {
         if (lane == 0) {
             mbar_init(&a_ready[0], 8); mbar_init(&a_ready[1], 8);
             mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
             mbar_init(w_bar, 1);
-            mbar_init(&ring_full[0], 1); mbar_init(&ring_full[1], 1);
-            mbar_init(&ring_empty[0], 1); mbar_init(&ring_empty[1], 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1);
+                mbar_init(&a0_full[i], MLP_GATHER_WARPS); mbar_init(&a0_empty[i], 1);
+            }
             fence_barrier_init();
+            *stop_flag = 0u;
+            tile_ids[0] = has_work ? blockIdx.x : MLP_NO_TILE;
         }
         __syncwarp();
         tmem_alloc(tmem_ptr, 512);
     }
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned long long *>(smem + MLP_OFF_TL) = 0ull;
-    for (uint32_t i = threadIdx.x; i < 3 * 128; i += MLP_THREADS) bias_s[i] = p.bias[i];
+    if (threadIdx.x < 2) reinterpret_cast<unsigned long long *>(smem + MLP_OFF_TL)[threadIdx.x] = 0ull;
+    if (p.timeline != nullptr && threadIdx.x == 0) {  // debug: per-CTA start time (ns)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[1000 + 8 * blockIdx.x] = t;
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.timeline[1000 + 8 * blockIdx.x + 4] = smid;
+        p.timeline[1000 + 8 * blockIdx.x + 7] = (unsigned long long)clock64();
+    }
     for (uint32_t i = threadIdx.x; i < 516; i += MLP_THREADS) head_s[i] = p.head[i];
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tbase = *tmem_ptr;
 
-    if (warp == 16) {
-        // ================= TMA: resident weights, then the L4 ring =================
-        if (lane == 0 && my_tiles > 0) {
-            mbar_arrive_expect_tx(w_bar, MLP_W_RESIDENT);
-            for (uint32_t off = 0; off < MLP_W_RESIDENT; off += 16384) tma_bulk_g2s(w_s + off, p.wimg + off, 16384, w_bar);
-            if (FINE) {
-                const uint8_t *w4 = p.wimg + MLP_W_RESIDENT;
-                const uint32_t nchunks = my_tiles * 4;
-                for (uint32_t i = 0; i < nchunks; ++i) {
-                    const uint32_t st = i & 1u;
-                    mbar_wait_backoff(&ring_empty[st], ((i >> 1) & 1u) ^ 1u, 128);
-                    mbar_arrive_expect_tx(&ring_full[st], 16384);
-                    tma_bulk_g2s(ring_s + st * 16384, w4 + (i & 3u) * 16384, 16384, &ring_full[st]);
+    if (warp >= 16 && warp < 20) {
+        reg_dec<MLP_REGS_CTRL>();
+        if (warp == 16) {
+            // ================= TMA: resident weights, then the L4 ring =================
+            if (lane == 0 && has_work) {
+                mbar_arrive_expect_tx(w_bar, MLP_W_RESIDENT);
+                for (uint32_t off = 0; off < MLP_W_RESIDENT; off += 16384) tma_bulk_g2s(w_s + off, p.wimg + off, 16384, w_bar);
+                if (FINE) {
+                    // keeps both stages filled (chunk i of the endless sequence hi0 lo0 hi1 lo1 ...) until the issuer says stop;
+                    // the one or two chunks fetched beyond the last tile are awaited before the CTA exits
+                    const uint8_t *w4 = p.wimg + MLP_W_RESIDENT;
+                    uint32_t st = 0, par = 1, i = 0;  // first round: the stages are empty (wait on the preceding phase passes)
+                    for (;; ++i) {
+                        bool stop = false;
+                        while (!mbar_test(&ring_empty[st], par)) {
+                            if (*stop_flag != 0u) { stop = true; break; }
+                            __nanosleep(64);
+                        }
+                        if (stop) break;
+                        mbar_arrive_expect_tx(&ring_full[st], MLP_RING_CHUNK);
+                        tma_bulk_g2s(ring_s + st * MLP_RING_CHUNK, w4 + (i & 3u) * MLP_RING_CHUNK, MLP_RING_CHUNK, &ring_full[st]);
+                        if (++st == MLP_RING_STAGES) { st = 0; par ^= 1u; }
+                    }
+                    const uint32_t fills0 = (i + 1u) / 2u, fills1 = i / 2u;  // fills of stage 0 / 1; phase f of ring_full = fill f
+                    if (fills0) mbar_wait_backoff(&ring_full[0], (fills0 - 1u) & 1u, 64);
+                    if (fills1) mbar_wait_backoff(&ring_full[1], (fills1 - 1u) & 1u, 64);
                 }
             }
-        }
-    } else if (warp == 17) {
-        // ================= MMA issuer (highest warp id: the arbiter favours it over the epilogue warps) =================
-        if (lane == 0 && my_tiles > 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 128);
-            // scalar per-slot state (no dynamically indexed arrays: they would live in local memory and every
-            // MMA issue would pay a local-memory round trip)
-            uint32_t left0 = ((my_tiles + 1) / 2) * (uint32_t)L, left1 = (my_tiles / 2) * (uint32_t)L;
-            uint32_t par0 = 0, par1 = 0, layer0 = 0, layer1 = 0, ring_par = 0;
-            mbar_wait(w_bar, 0);
-            // descriptor of byte offset `off` in the resident image = dw + (off >> 4); ring stage st = dr + st * 1024
-            const uint64_t dw = make_desc_sw128(smem_u32(w_s)), dr = make_desc_sw128(smem_u32(ring_s));
-            // one 64-wide K block: (A_hi,W_hi) (A_lo,W_hi) (A_hi,W_lo); descriptors differ by compile-time constants
-#define TN_KBLOCK(FIRST, DHI, DLO, KB)                                                                      \
-    mma_ts_c<!(FIRST)>(d_t, ahi + (KB) * 32u + 0u, (DHI) + 0ull, idesc);                                     \
-    mma_ts_c<true>(d_t, ahi + (KB) * 32u + 8u, (DHI) + 2ull, idesc);                                         \
-    mma_ts_c<true>(d_t, ahi + (KB) * 32u + 16u, (DHI) + 4ull, idesc);                                        \
-    mma_ts_c<true>(d_t, ahi + (KB) * 32u + 24u, (DHI) + 6ull, idesc);                                        \
-    mma_ts_c<true>(d_t, alo + (KB) * 32u + 0u, (DHI) + 0ull, idesc);                                         \
-    mma_ts_c<true>(d_t, alo + (KB) * 32u + 8u, (DHI) + 2ull, idesc);                                         \
-    mma_ts_c<true>(d_t, alo + (KB) * 32u + 16u, (DHI) + 4ull, idesc);                                        \
-    mma_ts_c<true>(d_t, alo + (KB) * 32u + 24u, (DHI) + 6ull, idesc);                                        \
-    mma_ts_c<true>(d_t, ahi + (KB) * 32u + 0u, (DLO) + 0ull, idesc);                                         \
-    mma_ts_c<true>(d_t, ahi + (KB) * 32u + 8u, (DLO) + 2ull, idesc);                                         \
-    mma_ts_c<true>(d_t, ahi + (KB) * 32u + 16u, (DLO) + 4ull, idesc);                                        \
-    mma_ts_c<true>(d_t, ahi + (KB) * 32u + 24u, (DLO) + 6ull, idesc);
-#define TN_SERVE(SLOT, LEFT, PAR, LAYER)                                                                     \
-    if (LEFT) {                                                                                              \
-        mbar_wait_backoff(&a_ready[SLOT], PAR, 32);                                                          \
-        fence_after_sync();                                                                                  \
-        const uint32_t l = LAYER;                                                                            \
-        const uint32_t d_t = tbase + 256u * (SLOT), ahi = d_t + 128u, alo = d_t + 192u;                      \
-        tl_mark(p.timeline, 0, 17, 1 + (SLOT), 0, l);                                                        \
-        if (l == 0) {                                                                                        \
-            TN_KBLOCK(true, dw, dw + 1024ull, 0u)                                                            \
-        } else if (l == 1) {                                                                                 \
-            TN_KBLOCK(true, dw + 2048ull, dw + 3072ull, 0u)                                                  \
-            TN_KBLOCK(false, dw + 4096ull, dw + 5120ull, 1u)                                                 \
-        } else if (l == 2) {                                                                                 \
-            TN_KBLOCK(true, dw + 6144ull, dw + 7168ull, 0u)                                                  \
-            TN_KBLOCK(false, dw + 8192ull, dw + 9216ull, 1u)                                                 \
-        } else {                                                                                             \
-            /* layer 4: chunks hi(kb0) lo(kb0) hi(kb1) lo(kb1) stream through the ring (hi -> stage 0, lo -> stage 1) */ \
-            mbar_wait(&ring_full[0], ring_par);                                                              \
-            mma_ts_c<false>(d_t, ahi + 0u, dr + 0ull, idesc); mma_ts_c<true>(d_t, ahi + 8u, dr + 2ull, idesc);   \
-            mma_ts_c<true>(d_t, ahi + 16u, dr + 4ull, idesc); mma_ts_c<true>(d_t, ahi + 24u, dr + 6ull, idesc);  \
-            mma_ts_c<true>(d_t, alo + 0u, dr + 0ull, idesc); mma_ts_c<true>(d_t, alo + 8u, dr + 2ull, idesc);    \
-            mma_ts_c<true>(d_t, alo + 16u, dr + 4ull, idesc); mma_ts_c<true>(d_t, alo + 24u, dr + 6ull, idesc);  \
-            mma_commit(&ring_empty[0]);                                                                      \
-            mbar_wait(&ring_full[1], ring_par);                                                              \
-            mma_ts_c<true>(d_t, ahi + 0u, dr + 1024ull, idesc); mma_ts_c<true>(d_t, ahi + 8u, dr + 1026ull, idesc);   \
-            mma_ts_c<true>(d_t, ahi + 16u, dr + 1028ull, idesc); mma_ts_c<true>(d_t, ahi + 24u, dr + 1030ull, idesc); \
-            mma_commit(&ring_empty[1]);                                                                      \
-            ring_par ^= 1u;                                                                                  \
-            mbar_wait(&ring_full[0], ring_par);                                                              \
-            mma_ts_c<true>(d_t, ahi + 32u, dr + 0ull, idesc); mma_ts_c<true>(d_t, ahi + 40u, dr + 2ull, idesc);  \
-            mma_ts_c<true>(d_t, ahi + 48u, dr + 4ull, idesc); mma_ts_c<true>(d_t, ahi + 56u, dr + 6ull, idesc);  \
-            mma_ts_c<true>(d_t, alo + 32u, dr + 0ull, idesc); mma_ts_c<true>(d_t, alo + 40u, dr + 2ull, idesc);  \
-            mma_ts_c<true>(d_t, alo + 48u, dr + 4ull, idesc); mma_ts_c<true>(d_t, alo + 56u, dr + 6ull, idesc);  \
-            mma_commit(&ring_empty[0]);                                                                      \
-            mbar_wait(&ring_full[1], ring_par);                                                              \
-            mma_ts_c<true>(d_t, ahi + 32u, dr + 1024ull, idesc); mma_ts_c<true>(d_t, ahi + 40u, dr + 1026ull, idesc); \
-            mma_ts_c<true>(d_t, ahi + 48u, dr + 1028ull, idesc); mma_ts_c<true>(d_t, ahi + 56u, dr + 1030ull, idesc); \
-            mma_commit(&ring_empty[1]);                                                                      \
-            ring_par ^= 1u;                                                                                  \
-        }                                                                                                    \
-        mma_commit(&d_ready[SLOT]);                                                                          \
-        tl_mark(p.timeline, 0, 17, 3 + (SLOT), 0, l);                                                        \
-        PAR ^= 1u;                                                                                           \
-        LAYER = (l + 1u) % (uint32_t)L;                                                                      \
-        LEFT--;                                                                                              \
-    }
-            while (left0 | left1) {  // strict alternation: the two slots run in lockstep, one slot's epilogue under the other's MMAs
-                TN_SERVE(0, left0, par0, layer0)
-                TN_SERVE(1, left1, par1, layer1)
+        } else if (warp == 17) {
+            // ================= MMA issuer =================
+            if (lane == 0 && has_work) {
+                MlpIssue s;
+                s.tbase = tbase;
+                s.bars = smem_u32(bars);
+                s.dw = desc_lo(smem_u32(w_s));
+                s.dr = desc_lo(smem_u32(ring_s));
+                s.da0 = desc_lo(smem_u32(smem + MLP_OFF_A0));
+                s.rst = 0; s.rpar = 0; s.nseq = 0; s.done = 0;
+                uint32_t par0 = 0, par1 = 0, layer0 = 0, layer1 = 0;
+                mbar_wait(w_bar, 0);
+                // strict alternation between the slots; slot 1 starts one round late so that the layer-0 passes (the consumers
+                // of the layer-0 operand buffer) are evenly spaced and each slot's epilogue runs under the other slot's MMAs
+                bool alive0 = mlp_serve<FINE, 0>(s, par0, layer0, p), alive1 = true;
+                while (alive0 | alive1) {
+                    if (alive0) alive0 = mlp_serve<FINE, 0>(s, par0, layer0, p);
+                    if (alive1) alive1 = mlp_serve<FINE, 1>(s, par1, layer1, p);
+                }
+                *stop_flag = 1u;
             }
-#undef TN_SERVE
-#undef TN_KBLOCK
+        }
+    } else if (warp >= (int)MLP_GATHER_WARP0) {
+        // ================= gather warps: interpolated features -> layer-0 A operand in shared memory =================
+        // warp g owns tile rows 32g..32g+31: 16 steps of two rows (one per half-warp, lane l16 -> features 4*l16..+3);
+        // lane i keeps the matched vertex ids / weights of row i; the vertex-row loads run 4 steps (16 x 16 B per lane)
+        // ahead of the interpolation, across tile boundaries.  Lane 0 of the first gather warp is the CTA's tile
+        // scheduler: it draws tile numbers from the global counter two tiles ahead and publishes them in tile_ids.
+        reg_inc<MLP_REGS_GATHER>();
+        if (has_work) {
+        const uint32_t g = (uint32_t)warp - MLP_GATHER_WARP0;
+        const bool sched = warp == (int)MLP_GATHER_WARP0 && lane == 0;
+        const uint32_t hw = (uint32_t)lane >> 4, l16 = (uint32_t)lane & 15u;
+        const float4 *fs = reinterpret_cast<const float4 *>(p.fshadow) + l16;  // a field row is 16 float4
+        uint4 cv, nv;
+        float cb0, cb1, cb2, nb0, nb1, nb2;
+#define TN_LOAD_IDS(TILE, V, B0, B1, B2)                                                                            \
+    {                                                                                                                \
+        V = make_uint4(TN_EMPTY, TN_EMPTY, TN_EMPTY, TN_EMPTY);                                                      \
+        B0 = 0.f; B1 = 0.f; B2 = 0.f;                                                                                \
+        if ((TILE) != MLP_NO_TILE) {                                                                                 \
+            const uint64_t gr = (uint64_t)(TILE) * 128u + g * 32u + (uint32_t)lane;                                  \
+            if (gr < total_rows) {                                                                                   \
+                V = __ldg(p.vi + gr);                                                                                \
+                B0 = __ldg(p.bary + 3 * gr); B1 = __ldg(p.bary + 3 * gr + 1); B2 = __ldg(p.bary + 3 * gr + 2);       \
+            }                                                                                                        \
+        }                                                                                                            \
+    }
+        float4 f[4][4];  // [pipeline buffer][vertex]
+#define TN_ISSUE(BUF, V, C)                                                                                          \
+    {                                                                                                                \
+        const int r_ = 2 * (C) + (int)hw;                                                                            \
+        const uint32_t v0 = __shfl_sync(0xffffffffu, V.x, r_), v1 = __shfl_sync(0xffffffffu, V.y, r_);               \
+        const uint32_t v2 = __shfl_sync(0xffffffffu, V.z, r_), v3 = __shfl_sync(0xffffffffu, V.w, r_);               \
+        const bool m_ = TN_MLP_GATHER_ON && v0 != TN_EMPTY;                                                          \
+        const float4 z_ = make_float4(0.f, 0.f, 0.f, 0.f);                                                           \
+        f[BUF][0] = m_ ? ldg_stream(fs + (size_t)v0 * 16) : z_;                                                      \
+        f[BUF][1] = m_ ? ldg_stream(fs + (size_t)v1 * 16) : z_;                                                      \
+        f[BUF][2] = m_ ? ldg_stream(fs + (size_t)v2 * 16) : z_;                                                      \
+        f[BUF][3] = m_ ? ldg_stream(fs + (size_t)v3 * 16) : z_;                                                      \
+    }
+        uint32_t cur = blockIdx.x, nxt = MLP_NO_TILE, pending = MLP_NO_TILE;
+        if (sched) pending = gridDim.x + atomicAdd(p.tile_ctr, 1u);  // tile of sequence number 1 (read one tile later)
+        TN_LOAD_IDS(cur, cv, cb0, cb1, cb2)
+        TN_ISSUE(0, cv, 0) TN_ISSUE(1, cv, 1) TN_ISSUE(2, cv, 2) TN_ISSUE(3, cv, 3)
+#if TN_MLP_STATS
+        long long dbg_wait = 0, dbg_busy = 0, dbg_t = 0;
+#endif
+        uint32_t n = 0;
+        for (; cur != MLP_NO_TILE; ++n) {
+            if (sched) {  // publish the tile of sequence number n+1, draw the one of n+2
+                const uint32_t v = pending < ntiles ? pending : MLP_NO_TILE;
+                tile_ids[(n + 1u) & 7u] = v;
+                if (v == MLP_NO_TILE) tile_ids[(n + 2u) & 7u] = MLP_NO_TILE;  // both slots must see the end
+                pending = v != MLP_NO_TILE ? gridDim.x + atomicAdd(p.tile_ctr, 1u) : MLP_NO_TILE;
+            }
+            asm volatile("bar.sync 3, 128;" ::: "memory");
+            nxt = tile_ids[(n + 1u) & 7u];
+            TN_LOAD_IDS(nxt, nv, nb0, nb1, nb2)
+            const uint32_t b = NBUF == 2 ? (n & 1u) : 0u;
+            const uint32_t a0 = smem_u32(smem + (b ? MLP_OFF_RING : MLP_OFF_A0));
+#if TN_MLP_STATS
+            if (p.timeline != nullptr) dbg_t = clock64();
+#endif
+            if (n >= NBUF) mbar_wait_backoff(&a0_empty[b], (n / NBUF - 1u) & 1u, 64);  // the layer-0 MMAs of the tile that used this buffer are done
+#if TN_MLP_STATS
+            if (p.timeline != nullptr) { const long long t = clock64(); dbg_wait += t - dbg_t; dbg_t = t; }
+#endif
+            if (p.timeline != nullptr && blockIdx.x == 0 && sched && n == 8)
+                reinterpret_cast<volatile unsigned long long *>(smem + MLP_OFF_TL)[1] = 1ull;  // steady state reached: start recording
+            tl_mark(p.timeline, lane, warp, 5, n, 0);  // ev 5: gather stores start
+            {
+#pragma unroll
+                for (int cc = 0; cc < 16; cc += 2) {
+#pragma unroll
+                    for (int c = cc; c < cc + 2; ++c) {
+                        const int r = 2 * c + (int)hw;
+                        const float b0 = __shfl_sync(0xffffffffu, cb0, r), b1 = __shfl_sync(0xffffffffu, cb1, r), b2 = __shfl_sync(0xffffffffu, cb2, r);
+                        const float4 *fc = f[c & 3];
+                        const float w0 = __fsub_rn(1.0f, __fadd_rn(__fadd_rn(b0, b1), b2));
+                        float4 o;  // tetrahedra_tracer.cu:203-220: v1*b0, + v2*b1, + v3*b2, + v0*w0 (fused multiply-adds)
+                        o.x = __fmaf_rn(b0, fc[1].x, 0.f); o.y = __fmaf_rn(b0, fc[1].y, 0.f); o.z = __fmaf_rn(b0, fc[1].z, 0.f); o.w = __fmaf_rn(b0, fc[1].w, 0.f);
+                        o.x = __fmaf_rn(b1, fc[2].x, o.x); o.y = __fmaf_rn(b1, fc[2].y, o.y); o.z = __fmaf_rn(b1, fc[2].z, o.z); o.w = __fmaf_rn(b1, fc[2].w, o.w);
+                        o.x = __fmaf_rn(b2, fc[3].x, o.x); o.y = __fmaf_rn(b2, fc[3].y, o.y); o.z = __fmaf_rn(b2, fc[3].z, o.z); o.w = __fmaf_rn(b2, fc[3].w, o.w);
+                        o.x = __fmaf_rn(w0, fc[0].x, o.x); o.y = __fmaf_rn(w0, fc[0].y, o.y); o.z = __fmaf_rn(w0, fc[0].z, o.z); o.w = __fmaf_rn(w0, fc[0].w, o.w);
+                        uint32_t h0, l0, h1, l1;
+                        split_pack2(o.x, o.y, h0, l0);
+                        split_pack2(o.z, o.w, h1, l1);
+                        // tile row R = 32 g + 2 c + hw inside the swizzled [128][64] bf16 block
+                        const uint32_t R = g * 32u + (uint32_t)r, r7 = R & 7u;
+                        const uint32_t addr = a0 + (R >> 3) * 1024u + r7 * 128u + (((l16 >> 1) ^ r7) << 4) + (l16 & 1u) * 8u;
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(h0), "r"(h1) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + 16384u), "r"(l0), "r"(l1) : "memory");
+                    }
+                    // refill the two pipeline buffers just consumed: 4 steps ahead, running into the next tile at the end of this one
+                    if (cc + 4 < 16) { TN_ISSUE(cc & 3, cv, cc + 4) TN_ISSUE((cc + 1) & 3, cv, cc + 5) }
+                    else { TN_ISSUE(cc & 3, nv, cc + 4 - 16) TN_ISSUE((cc + 1) & 3, nv, cc + 5 - 16) }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a0_full[b]);
+            tl_mark(p.timeline, lane, warp, 6, n, 0);  // ev 6: operand stored, arrived
+#if TN_MLP_STATS
+            if (p.timeline != nullptr) dbg_busy += clock64() - dbg_t;
+#endif
+            cur = nxt; cv = nv; cb0 = nb0; cb1 = nb1; cb2 = nb2;
+        }
+        {   // sequence number n is the first one without a tile: complete its "operand ready" phase (after the buffer's
+            // previous consumer, like a real tile) so that the issuer wakes up, reads the sentinel and retires the slots
+            const uint32_t b = NBUF == 2 ? (n & 1u) : 0u;
+            if (n >= NBUF) mbar_wait_backoff(&a0_empty[b], (n / NBUF - 1u) & 1u, 64);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a0_full[b]);
+        }
+#if TN_MLP_STATS
+        if (p.timeline != nullptr && sched) {
+            p.timeline[1000 + 8 * blockIdx.x + 5] = (unsigned long long)dbg_busy;
+            p.timeline[1000 + 8 * blockIdx.x + 6] = (unsigned long long)dbg_wait;
+        }
+#endif
+#undef TN_ISSUE
+#undef TN_LOAD_IDS
         }
     } else {
-        // ================= slot warps: gather -> A0, per-layer epilogues, heads =================
+        // ================= slot warps: per-layer epilogues, heads =================
+        reg_inc<MLP_REGS_WORKER>();
         const int slot = warp >> 3;
         const uint32_t h = (uint32_t)(warp >> 2) & 1u;  // column half
-        const uint32_t q = (uint32_t)warp & 3u;               // TMEM lane quarter this warp may access
+        const uint32_t q = (uint32_t)warp & 3u;         // TMEM lane quarter this warp may access
         const uint32_t lane_base = (q * 32u) << 16;
         const uint32_t d_t = tbase + 256u * slot + lane_base, ahi = d_t + 128u, alo = d_t + 192u;
-        float *stage = reinterpret_cast<float *>(smem + MLP_OFF_STAGE) + (size_t)warp * 4 * MLP_STAGE_STRIDE;
-        float *dirb = dirb_s + slot * 4 * 128;
-        float4 *red = red_s + slot * 128;
         const float *wd = head_s, *wc = head_s + 128;
-        const uint32_t hw = (uint32_t)lane >> 4, l16 = (uint32_t)lane & 15u;
-        uint32_t dpar = 0;
-        for (uint32_t it = slot; it < my_tiles; it += 2) {
-            const uint64_t tile_row0 = (uint64_t)(blockIdx.x + (uint64_t)it * gridDim.x) * 128u;
-            const uint64_t warp_row0 = tile_row0 + q * 32u;
-            // ---- gather + barycentric interpolation (tetrahedra_tracer.cu:203-220) ----
-            // lane i first fetches the matched vertex ids / weights of row i (one coalesced load per warp), then the
-            // rows are processed 4 at a time (2 per half-warp, lanes over the 32 features of this column half) with the
-            // vertex-row loads of the next step in flight while the current step is interpolated and transposed.
-            uint4 myv = make_uint4(TN_EMPTY, TN_EMPTY, TN_EMPTY, TN_EMPTY);
-            float myb0 = 0.f, myb1 = 0.f, myb2 = 0.f;
-            {
-                const uint64_t g = warp_row0 + lane;
-                if (g < total_rows) {
-                    myv = __ldg(p.vi + g);
-                    myb0 = __ldg(p.bary + 3 * g); myb1 = __ldg(p.bary + 3 * g + 1); myb2 = __ldg(p.bary + 3 * g + 2);
-                }
-            }
-            tl_mark(p.timeline, lane, warp, 5, it, 0);    // ev 5: gather start
-            uint32_t hi[16], lo[16];
-            float2 f[2][2][4];  // [buffer][sample of this half-warp][vertex]
-            const float2 *fs = reinterpret_cast<const float2 *>(p.fshadow + h * 32) + l16;
-#define TN_ISSUE(BUF, C)                                                                                              \
-    _Pragma("unroll") for (int j = 0; j < 2; ++j) {                                                                   \
-        const int r = 4 * (C) + 2 * j + (int)hw;                                                                      \
-        const uint32_t v0 = __shfl_sync(0xffffffffu, myv.x, r), v1 = __shfl_sync(0xffffffffu, myv.y, r);              \
-        const uint32_t v2 = __shfl_sync(0xffffffffu, myv.z, r), v3 = __shfl_sync(0xffffffffu, myv.w, r);              \
-        const bool m = v0 != TN_EMPTY;                                                                                \
-        f[BUF][j][0] = m ? __ldg(fs + (size_t)v0 * 32) : make_float2(0.f, 0.f);                                       \
-        f[BUF][j][1] = m ? __ldg(fs + (size_t)v1 * 32) : make_float2(0.f, 0.f);                                       \
-        f[BUF][j][2] = m ? __ldg(fs + (size_t)v2 * 32) : make_float2(0.f, 0.f);                                       \
-        f[BUF][j][3] = m ? __ldg(fs + (size_t)v3 * 32) : make_float2(0.f, 0.f);                                       \
-    }
-            TN_ISSUE(0, 0)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c + 1 < 8) {
-                    if ((c & 1) == 0) { TN_ISSUE(1, c + 1) } else { TN_ISSUE(0, c + 1) }
-                }
-                __syncwarp();  // previous step's readers are done with the staging rows
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int r = 4 * c + 2 * j + (int)hw;
-                    const float b0 = __shfl_sync(0xffffffffu, myb0, r), b1 = __shfl_sync(0xffffffffu, myb1, r), b2 = __shfl_sync(0xffffffffu, myb2, r);
-                    const float2 *fc = f[c & 1][j];
-                    const float w0 = __fsub_rn(1.0f, __fadd_rn(__fadd_rn(b0, b1), b2));
-                    float2 o;
-                    o.x = __fmaf_rn(b0, fc[1].x, 0.f); o.y = __fmaf_rn(b0, fc[1].y, 0.f);
-                    o.x = __fmaf_rn(b1, fc[2].x, o.x); o.y = __fmaf_rn(b1, fc[2].y, o.y);
-                    o.x = __fmaf_rn(b2, fc[3].x, o.x); o.y = __fmaf_rn(b2, fc[3].y, o.y);
-                    o.x = __fmaf_rn(w0, fc[0].x, o.x); o.y = __fmaf_rn(w0, fc[0].y, o.y);
-                    reinterpret_cast<float2 *>(stage + (2 * j + hw) * MLP_STAGE_STRIDE)[l16] = o;
-                }
-                __syncwarp();
-                if ((lane >> 2) == c) {  // lanes 4c..4c+3 own rows 4c..4c+3 of this warp's 32 rows
-                    const float4 *rowp = reinterpret_cast<const float4 *>(stage + (lane & 3) * MLP_STAGE_STRIDE);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 x = rowp[i];
-                        split_pack2(x.x, x.y, hi[2 * i], lo[2 * i]);
-                        split_pack2(x.z, x.w, hi[2 * i + 1], lo[2 * i + 1]);
-                    }
-                }
-            }
-#undef TN_ISSUE
-            tmem_st16(ahi + 16 * h, hi);
-            tmem_st16(alo + 16 * h, lo);
-            tmem_st_wait();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[slot]);
-            tl_mark(p.timeline, lane, warp, 6, it, 0);    // ev 6: A0 written, arrived
-
-            // ---- FINE: stage the per-ray direction bias of the (few) rays this tile touches ----
-            const uint64_t my_row = warp_row0 + lane;
+        uint32_t dpar = 0, ntl = 0;
+        if (has_work) {
+        if (lane == 0) mbar_arrive(&a_ready[slot]);  // the slot's accumulator is free for the first tile
+        for (uint32_t n = slot;; n += 2) {            // the slot handles the CTA's tiles of sequence number n = slot, slot + 2, ...
+            uint32_t tile = MLP_NO_TILE;
+            uint64_t my_row = 0;
             const float *bias4 = nullptr;
-            if (FINE) {
-                const uint32_t ray0 = (uint32_t)(tile_row0 / p.S);
-                const uint64_t last_row = min(tile_row0 + 127, total_rows - 1);
-                const uint32_t nr = (uint32_t)(last_row / p.S) - ray0 + 1;
-                const uint32_t my_ray_off = (uint32_t)(min(my_row, total_rows - 1) / p.S) - ray0;
-                if (nr <= 4) {
-                    for (uint32_t i = (warp & 7) * 32 + lane; i < nr * 128; i += 256) dirb[i] = __ldg(p.dirbias + (size_t)ray0 * 128 + i);
-                    asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
-                    bias4 = dirb + my_ray_off * 128;
-                } else {
-                    bias4 = p.dirbias + (size_t)(ray0 + my_ray_off) * 128;  // many short rays per tile: read the bias from L2
-                }
-            }
-
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int l = 0; l < L; ++l) {
-                tl_mark(p.timeline, lane, warp, 7, it, l);  // ev 7: start waiting for D
+                tl_mark(p.timeline, lane, warp, 7, n, l);  // ev 7: start waiting for D
                 mbar_wait_backoff(&d_ready[slot], dpar, 32);
                 dpar ^= 1u;
                 fence_after_sync();
-                tl_mark(p.timeline, lane, warp, 8, it, l);  // ev 8: D ready seen
-                if (l < 2) layer_epilogue<0>(d_t, ahi, alo, h, bias_s + l * 128, wd, wc, acc);
-                else if (l == 2 && FINE) layer_epilogue<1>(d_t, ahi, alo, h, bias_s + 256, wd, wc, acc);
-                else if (l == 2) layer_epilogue<2>(d_t, ahi, alo, h, bias_s + 256, wd, wc, acc);
+                tl_mark(p.timeline, lane, warp, 8, n, l);  // ev 8: D ready seen
+                if (l == 0) {
+                    tile = tile_ids[n & 7u];
+                    if (tile == MLP_NO_TILE) break;  // retired by the issuer
+                    ++ntl;
+                    my_row = (uint64_t)tile * 128u + q * 32u + (uint32_t)lane;
+                    if (FINE) {  // per-ray direction bias of this thread's row (read through L1 in the last epilogue; warm the line now)
+                        bias4 = p.dirbias + (size_t)(min(my_row, total_rows - 1) / p.S) * 128;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(bias4 + ((uint32_t)lane & 3u) * 32u));
+                    }
+                }
+                if (l < 2) layer_epilogue<0>(d_t, ahi, alo, h, p.bias + l * 128, wd, wc, acc);
+                else if (l == 2 && FINE) layer_epilogue<1>(d_t, ahi, alo, h, p.bias + 256, wd, wc, acc);
+                else if (l == 2) layer_epilogue<2>(d_t, ahi, alo, h, p.bias + 256, wd, wc, acc);
                 else layer_epilogue<3>(d_t, ahi, alo, h, bias4, wd, wc, acc);
-                if (l < L - 1) {
-                    tmem_st_wait();
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_ready[slot]);
-                }
-                tl_mark(p.timeline, lane, warp, 9, it, l);  // ev 9: epilogue of layer l done (+arrive)
+                // next A operand written (l < L-1) / accumulator read out and free for the next tile (l == L-1)
+                if (l < L - 1) tmem_st_wait();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[slot]);
+                tl_mark(p.timeline, lane, warp, 9, n, l);  // ev 9: epilogue of layer l done (+arrive)
             }
+            if (tile == MLP_NO_TILE) break;
             // ---- heads: combine the two column halves, activation, store ----
-            if (h == 1) red[q * 32 + lane] = acc;
+            // The partial sums of the upper column half travel through TMEM: the first four columns of the slot's A region
+            // (dead once the last layer's MMAs are done; next written by this lane quarter's h == 0 warp itself, in the
+            // next tile's first epilogue).
+            if (h == 1) {
+                tmem_st4(ahi, reinterpret_cast<const uint32_t *>(&acc));
+                tmem_st_wait();
+                fence_before_sync();
+            }
             asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
-            if (h == 0 && my_row < total_rows) {
-                const float4 o = red[q * 32 + lane];
-                const float sigma = softplus_f(acc.x + o.x + head_s[512]);
-                if (FINE) {
-                    reinterpret_cast<float4 *>(p.out)[my_row] = make_float4(sigma, sigmoid_f(acc.y + o.y + head_s[513]),
-                                                                           sigmoid_f(acc.z + o.z + head_s[514]), sigmoid_f(acc.w + o.w + head_s[515]));
-                } else {
-                    p.out[my_row] = sigma;
+            if (h == 0) {
+                fence_after_sync();
+                float4 o;
+                tmem_ld4(ahi, reinterpret_cast<uint32_t *>(&o));
+                tmem_ld_wait();
+                if (my_row < total_rows) {
+                    const float sigma = softplus_f(acc.x + o.x + head_s[512]);
+                    if (FINE) {
+                        reinterpret_cast<float4 *>(p.out)[my_row] = make_float4(sigma, sigmoid_f(acc.y + o.y + head_s[513]),
+                                                                               sigmoid_f(acc.z + o.z + head_s[514]), sigmoid_f(acc.w + o.w + head_s[515]));
+                    } else {
+                        p.out[my_row] = sigma;
+                    }
                 }
             }
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");  // red / dirb reuse by the next tile
         }
+        }
+        if (p.timeline != nullptr && threadIdx.x == 0) p.timeline[1000 + 8 * blockIdx.x + 3] = ntl;
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 16) tmem_dealloc(tbase, 512);
+    if (p.timeline != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[1000 + 8 * blockIdx.x + 1] = t;
+        p.timeline[1000 + 8 * blockIdx.x + 7] = (unsigned long long)clock64() - p.timeline[1000 + 8 * blockIdx.x + 7];
+    }
     if (p.timeline != nullptr && blockIdx.x == 0) {
         const unsigned long long *tl = reinterpret_cast<const unsigned long long *>(smem + MLP_OFF_TL);
         const uint32_t n = (uint32_t)min(tl[0], (unsigned long long)MLP_TL_CAP);
-        for (uint32_t i = threadIdx.x; i <= n; i += MLP_THREADS) p.timeline[i] = i == 0 ? (unsigned long long)n : tl[i];
+        for (uint32_t i = threadIdx.x; i <= n; i += MLP_THREADS) p.timeline[i] = i == 0 ? (unsigned long long)n : tl[i + 1];
     }
 }
 

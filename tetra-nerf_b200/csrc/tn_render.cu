@@ -540,6 +540,7 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     MlpParams mc{};
     mc.n_active = r->n_active; mc.S = Sc; mc.vi = r->vi_c; mc.bary = r->bary_c; mc.fshadow = r->fshadow; mc.wimg = r->wimg;
     mc.bias = r->bias; mc.head = r->head; mc.dirbias = nullptr; mc.out = r->dens_c;
+    mc.tile_ctr = r->n_active + 1;  // words 1, 2 of the zeroed 16-byte block: tile counters of the coarse / fine pass
     const uint32_t tiles_c = (uint32_t)(((uint64_t)R * Sc + 127) / 128), tiles_f = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
     k_mlp<false><<<std::min<uint32_t>(tiles_c, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mc);
     TN_EV(3);
@@ -548,6 +549,7 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     MlpParams mf = mc;
     mf.S = S2; mf.vi = r->vi_f; mf.bary = r->bary_f; mf.dirbias = r->dirbias; mf.out = r->out_f;
     mf.timeline = g_timeline;
+    mf.tile_ctr = r->n_active + 2;
     k_mlp<true><<<std::min<uint32_t>(tiles_f, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mf);
     TN_EV(5);
     k_composite<<<gridR, SAMPLE_WARPS * 32, smem_c, s>>>(p);

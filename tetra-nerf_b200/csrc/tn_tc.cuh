@@ -41,6 +41,25 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
     while (!mbar_test(bar, parity)) __nanosleep(ns);
 }
 
+// variants taking the 32-bit shared-memory address of the barrier (the MMA issuer keeps no generic pointers)
+__device__ __forceinline__ bool mbar_test_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    while (!mbar_test_a(bar, parity)) {}
+}
+__device__ __forceinline__ void mbar_wait_backoff_a(uint32_t bar, uint32_t parity, uint32_t ns) {
+    while (!mbar_test_a(bar, parity)) __nanosleep(ns);
+}
+
 // ---- TMA bulk copy global -> shared (1-D, no tensor map) -----------------------------------------
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -87,9 +106,46 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+template <bool ACC>
+__device__ __forceinline__ void mma_ss_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+// Issue forms used by the fused MLP kernel.  They take BASE values plus compile-time offsets: the TMEM address of the
+// A operand is a_base + AOFF, the shared-memory descriptors are built from the LOW word (start address >> 4) base + OFF
+// and a constant high word (the same for every 128-byte-swizzle K-major operand).  The additions and the 64-bit
+// descriptor assembly happen inside the asm block, so the compiler sees only the few base registers -- with dozens of
+// unrolled MMAs it otherwise hoists every "base + constant" into a register, runs out, and parks them in local memory
+// (one LDL per MMA on the issue path).
+#define TN_DESC_HI_SW128 "0x40004040"   // SBO 1024 B (>>4) | version 1 (bit 46) | SWIZZLE_128B (2 << 61)
+template <bool ACC, uint32_t AOFF, uint32_t BOFF>
+__device__ __forceinline__ void mma_ts_o(uint32_t d_tmem, uint32_t a_base, uint32_t b_base_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 hi, ta, tb;\n\t.reg .b64 db;\n\t"
+        "setp.eq.u32 p, 1, %6;\n\tadd.u32 ta, %1, %4;\n\tadd.u32 tb, %2, %5;\n\tmov.u32 hi, " TN_DESC_HI_SW128 ";\n\tmov.b64 db, {tb, hi};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_base), "r"(b_base_lo), "r"(idesc), "n"(AOFF), "n"(BOFF), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+template <bool ACC, uint32_t AOFF, uint32_t BOFF>
+__device__ __forceinline__ void mma_ss_o(uint32_t d_tmem, uint32_t a_base_lo, uint32_t b_base_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 hi, ta, tb;\n\t.reg .b64 da, db;\n\t"
+        "setp.eq.u32 p, 1, %6;\n\tadd.u32 ta, %1, %4;\n\tadd.u32 tb, %2, %5;\n\tmov.u32 hi, " TN_DESC_HI_SW128 ";\n\tmov.b64 da, {ta, hi};\n\tmov.b64 db, {tb, hi};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_base_lo), "r"(b_base_lo), "r"(idesc), "n"(AOFF), "n"(BOFF), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr & 0x3FFFFu) >> 4; }
 // all previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mma_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // instruction descriptor, kind::f16: bf16 x bf16 -> f32, A and B K-major, M=128, N given
@@ -141,6 +197,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
