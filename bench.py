@@ -283,7 +283,7 @@ def main():
                         note="algorithmic fp32-equivalent FLOPs (SURVEY §8d); the kernel issues 3 bf16 MMAs per algorithmic MAC (bf16x3), "
                              "so tensor-pipe occupancy is ~3x this fraction")
         else:  # traversal dominates: HBM accounting of SURVEY §8d is filled by the ncu pass
-            roof.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=None, frac=None)
+            roof.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], peak_src=pk["src"] + " HBM copy", achieved=None, frac=None)
         prof = ROOT / "profiles" / "roofline_traffic.json"
         if prof.exists():
             try:

@@ -55,6 +55,38 @@ def test_faces_numbering(small_mesh, cube_mesh):
         assert np.array_equal(tt.cpu().numpy().view(np.uint32), ott)
 
 
+def test_faces_numbering_large_and_permuted():
+    """The device build (sort + scan, tn_faces.cu) must reproduce the reference's first-appearance numbering
+    (tetrahedra_tracer.cpp:45-63) -- which depends on the order of the tetrahedra and of the vertices inside each."""
+    V, C = syn.delaunay_mesh(6000, seed=4)
+    rng = np.random.default_rng(0)
+    C2 = C[rng.permutation(len(C))].copy()
+    for i in range(len(C2)):
+        C2[i] = C2[i][rng.permutation(4)]
+    for cells in (C, C2):
+        tr = make_tracer(V, cells)
+        tri, tt = tr.get_faces()
+        otri, ott = orc.OracleMesh(V, cells).faces()
+        assert tr.num_faces() == len(otri)
+        assert np.array_equal(tri.cpu().numpy().view(np.uint32), otri)
+        assert np.array_equal(tt.cpu().numpy().view(np.uint32), ott)
+
+
+def test_face_build_errors(cube_mesh):
+    """tetrahedra_tracer.cpp:64-66 (a triangle with a third owner) and an out-of-range vertex index."""
+    from tetranerf import cpp
+    V, C = cube_mesh
+    tr = cpp.TetrahedraTracer(DEV)
+    bad = np.concatenate([C, C[:1], C[:1]]).astype(C.dtype)  # the first tetrahedron three times
+    with pytest.raises(Exception, match="shared by more than two"):
+        tr.load_tetrahedra(torch.from_numpy(V).to(DEV), torch.from_numpy(bad).to(DEV))
+    bad2 = C.copy(); bad2[3, 2] = len(V) + 5
+    with pytest.raises(Exception, match="out of range"):
+        tr.load_tetrahedra(torch.from_numpy(V).to(DEV), torch.from_numpy(bad2).to(DEV))
+    tr.load_tetrahedra(torch.from_numpy(V).to(DEV), torch.from_numpy(C).to(DEV))  # the tracer is still usable
+    assert tr.num_faces() == 30
+
+
 def test_cube_known_answer(cube_mesh):
     V, C = cube_mesh
     tr = make_tracer(V, C)

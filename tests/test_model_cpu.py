@@ -75,3 +75,31 @@ def test_compat_layers_match_oracle_restatement():
     f = torch.randn(5, 9, 64)
     torch.testing.assert_close(m.mlp_base(f), orc.mlp_base(p, f))
     torch.testing.assert_close(m.field_output_density(m.mlp_base(f)), orc.density_head(p, orc.mlp_base(p, f)))
+
+
+def test_th_file_loader_and_dataparser_transform(tmp_path, small_mesh):
+    """`.th` input ({"vertices","cells","colors"}, scripts/triangulate.py:68-75) -> config sizes (model.py:102-107),
+    vertices through the dataparser transform + scale, colour/alpha initialisation of the field (model.py:343-392)."""
+    V, C = small_mesh
+    rng = np.random.default_rng(3)
+    colors = rng.integers(0, 256, size=(len(V), 4), dtype=np.uint8)
+    path = tmp_path / "scene.th"
+    torch.save({"vertices": torch.from_numpy(V), "cells": torch.from_numpy(C.astype(np.int32)), "colors": torch.from_numpy(colors)}, path)
+    cfg = M.TetrahedraNerfConfig(tetrahedra_path=path)
+    assert (cfg.num_tetrahedra_vertices, cfg.num_tetrahedra_cells) == (len(V), len(C))
+    with pytest.raises(RuntimeError, match="does not exist"):
+        M.TetrahedraNerfConfig(tetrahedra_path=tmp_path / "missing.th")
+    T = torch.tensor([[0.0, -1.0, 0.0, 0.5], [1.0, 0.0, 0.0, -0.25], [0.0, 0.0, 1.0, 2.0]])  # [3,4] rotation + translation
+    m = M.TetrahedraNerf(cfg, dataparser_transform=T, dataparser_scale=0.5)
+    assert not m._tetrahedra_initialized
+    m._init_tetrahedra()
+    want = (np.concatenate([V, np.ones((len(V), 1), np.float32)], 1) @ T.numpy().T) * 0.5
+    assert np.allclose(m.tetrahedra_vertices.numpy(), want, atol=1e-6)
+    assert np.array_equal(m.tetrahedra_cells.numpy(), C.astype(np.int32))
+    f = m.tetrahedra_field.detach().numpy()
+    assert np.allclose(f[1:4].T, colors[:, :3].astype(np.float32) * 2 / 255 - 1, atol=1e-6)
+    assert np.allclose(f[0], colors[:, 3].astype(np.float32) * 2 / 255 - 1, atol=1e-6)
+    assert np.abs(f[4:]).max() <= 1e-4  # uniform(-1e-4, 1e-4) everywhere else
+    m_no_pipe = M.TetrahedraNerf(cfg)
+    with pytest.raises(RuntimeError, match="dataparser_scale"):
+        m_no_pipe._init_tetrahedra()  # model.py:352-356

@@ -8,135 +8,11 @@
 
 #include <algorithm>
 #include <cmath>
-#include <unordered_map>
 #include <vector>
 
 #include "tn_common.cuh"
 
 namespace tn {
-
-// ---- unique faces, reference numbering (src/tetrahedra_tracer.cpp:21-71) -----------------------
-struct Key3 {
-    uint32_t a, b, c;
-    bool operator==(const Key3 &o) const { return a == o.a && b == o.b && c == o.c; }
-};
-struct Key3Hash {
-    size_t operator()(const Key3 &k) const {
-        uint64_t h = (uint64_t)k.a * 0x9E3779B97F4A7C15ull;
-        h = (h ^ (h >> 29)) + (uint64_t)k.b * 0xBF58476D1CE4E5B9ull;
-        h = (h ^ (h >> 31)) + (uint64_t)k.c * 0x94D049BB133111EBull;
-        return (size_t)(h ^ (h >> 32));
-    }
-};
-static inline Key3 sorted3(uint32_t x, uint32_t y, uint32_t z) {
-    if (x > y) std::swap(x, y);
-    if (y > z) std::swap(y, z);
-    if (x > y) std::swap(x, y);
-    return Key3{x, y, z};
-}
-
-// host pass: tri[F] (stored winding, padded to uint4), tt[F], tet_faces[T] (face id | owner<<31)
-static int unique_faces_host(const std::vector<uint32_t> &cells, uint32_t T, std::vector<uint4> &tri, std::vector<uint2> &tt,
-                             std::vector<uint4> &tet_faces) {
-    std::unordered_map<Key3, uint32_t, Key3Hash> known;
-    known.reserve((size_t)T * 2 + 16);
-    tet_faces.resize(T);
-    for (uint32_t i = 0; i < T; ++i) {
-        const uint32_t *c = &cells[4 * (size_t)i];
-        uint32_t fid[4];
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t x = c[(j + 1) & 3], y = c[(j + 2) & 3], z = c[(j + 3) & 3];
-            const Key3 key = sorted3(x, y, z);
-            auto it = known.find(key);
-            if (it == known.end()) {
-                const uint32_t id = (uint32_t)tt.size();
-                known.emplace(key, id);
-                tri.push_back(make_uint4(x, y, z, 0u));
-                tt.push_back(make_uint2(i, TN_EMPTY));
-                fid[j] = id | 0x80000000u;  // first owner: the stored winding is this rotation
-            } else {
-                if (tt[it->second].y != TN_EMPTY) return -1;
-                tt[it->second].y = i;
-                fid[j] = it->second;
-            }
-        }
-        tet_faces[i] = make_uint4(fid[0], fid[1], fid[2], fid[3]);
-    }
-    return 0;
-}
-
-// adjacency tables for the walk: neighbour across each face, stored winding as local vertex indices, hull flags
-static void walk_tables_host(const std::vector<uint32_t> &cells, uint32_t T, const std::vector<uint4> &tri, const std::vector<uint2> &tt,
-                             std::vector<uint4> &tet_faces, std::vector<uint4> &nbr, std::vector<uint32_t> &wind, std::vector<uint32_t> &hull_tets) {
-    nbr.resize(T); wind.resize(T);
-    for (uint32_t i = 0; i < T; ++i) {
-        const uint32_t *c = &cells[4 * (size_t)i];
-        uint32_t *fw = &tet_faces[i].x, *nb = &nbr[i].x;
-        uint32_t w = 0;
-        bool hull = false;
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t f = fw[j] & TN_FACE_MASK;
-            const uint2 o = tt[f];
-            nb[j] = (o.x == i) ? o.y : o.x;
-            if (o.y == TN_EMPTY) { fw[j] |= TN_FACE_HULL; hull = true; }
-            const uint32_t g[3] = {tri[f].x, tri[f].y, tri[f].z};
-            for (int k = 0; k < 3; ++k) {
-                uint32_t loc = 0;
-                for (uint32_t q = 0; q < 4; ++q) if (c[q] == g[k]) loc = q;
-                w |= loc << (6 * j + 2 * k);
-            }
-        }
-        wind[i] = w;
-        if (hull) hull_tets.push_back(i);
-    }
-}
-
-// the hull is convex iff across every hull edge the opposite vertex of one hull face is not above the plane of the other
-static bool hull_is_convex_host(const std::vector<float> &xyz, const std::vector<uint4> &tri, const std::vector<uint2> &tt,
-                                const std::vector<uint32_t> &cells) {
-    struct EdgeKey { uint64_t k; bool operator==(const EdgeKey &o) const { return k == o.k; } };
-    struct EdgeHash { size_t operator()(const EdgeKey &e) const { return (size_t)(e.k * 0x9E3779B97F4A7C15ull >> 17); } };
-    std::unordered_map<EdgeKey, uint32_t, EdgeHash> first;  // edge -> first hull face seen
-    auto P = [&](uint32_t v, int a) { return (double)xyz[3 * (size_t)v + a]; };
-    auto check = [&](uint32_t f, uint32_t g) -> bool {
-        // outward normal of hull face f: away from its tetrahedron's 4th vertex
-        const uint32_t t = tt[f].x;
-        const uint32_t fv[3] = {tri[f].x, tri[f].y, tri[f].z};
-        uint32_t inner = 0;
-        for (int q = 0; q < 4; ++q) { const uint32_t v = cells[4 * (size_t)t + q]; if (v != fv[0] && v != fv[1] && v != fv[2]) inner = v; }
-        double e1[3], e2[3], n[3];
-        for (int a = 0; a < 3; ++a) { e1[a] = P(fv[1], a) - P(fv[0], a); e2[a] = P(fv[2], a) - P(fv[0], a); }
-        n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
-        double si = 0, nn = 0;
-        for (int a = 0; a < 3; ++a) { si += n[a] * (P(inner, a) - P(fv[0], a)); nn += n[a] * n[a]; }
-        if (si > 0) for (int a = 0; a < 3; ++a) n[a] = -n[a];
-        const uint32_t gv[3] = {tri[g].x, tri[g].y, tri[g].z};
-        for (int k = 0; k < 3; ++k) {
-            double sd = 0, dd = 0;
-            for (int a = 0; a < 3; ++a) { const double d = P(gv[k], a) - P(fv[0], a); sd += n[a] * d; dd += d * d; }
-            if (sd > 1e-9 * std::sqrt(nn * dd) + 1e-30) return false;  // a vertex of the neighbouring hull face lies outside
-        }
-        return true;
-    };
-    for (uint32_t f = 0; f < (uint32_t)tri.size(); ++f) {
-        if (tt[f].y != TN_EMPTY) continue;
-        const uint32_t v[3] = {tri[f].x, tri[f].y, tri[f].z};
-        for (int k = 0; k < 3; ++k) {
-            uint32_t a = v[k], b = v[(k + 1) % 3];
-            if (a > b) std::swap(a, b);
-            const EdgeKey key{((uint64_t)a << 32) | b};
-            auto it = first.find(key);
-            if (it == first.end()) first.emplace(key, f);
-            else {
-                if (it->second == TN_EMPTY) return false;  // hull edge shared by more than two hull faces
-                if (!check(f, it->second) || !check(it->second, f)) return false;
-                it->second = TN_EMPTY;
-            }
-        }
-    }
-    for (auto &kv : first) if (kv.second != TN_EMPTY) return false;  // open hull edge
-    return true;
-}
 
 // ---- device kernels --------------------------------------------------------------------------
 __device__ __forceinline__ int f2ord(float f) {
@@ -296,34 +172,20 @@ int build_mesh(tn_tracer *h, const float *d_xyz, uint32_t V, const uint32_t *d_c
     if (T >= (1u << 28)) return fail(TN_ERR_ARG, "load_tetrahedra: more than 2^28 tetrahedra are not supported");
     Mesh &m = h->mesh;
 
-    // ---- faces (host pass, like the reference; the device build is a "next" row) ----
-    std::vector<uint32_t> hc((size_t)T * 4);
-    TN_CUDA(cudaMemcpyAsync(hc.data(), d_cells, sizeof(uint32_t) * 4 * (size_t)T, cudaMemcpyDeviceToHost, s));
-    TN_CUDA(cudaStreamSynchronize(s));
-    for (size_t i = 0; i < hc.size(); ++i)
-        if (hc[i] >= V) return fail(TN_ERR_ARG, "load_tetrahedra: cell index out of range");
-    std::vector<uint4> tri, tet_faces;
-    std::vector<uint2> tt;
-    tri.reserve((size_t)T * 2 + 16);
-    tt.reserve((size_t)T * 2 + 16);
-    if (unique_faces_host(hc, T, tri, tt, tet_faces) != 0)
-        return fail(TN_ERR_MESH, "A triangle is shared by more than two tetrahedra!");  // tetrahedra_tracer.cpp:64-66
-    const uint32_t F = (uint32_t)tri.size();
-    std::vector<uint4> nbr;
-    std::vector<uint32_t> wind, hull_tets;
-    walk_tables_host(hc, T, tri, tt, tet_faces, nbr, wind, hull_tets);
-    bool walkable = false;
+    // ---- faces, adjacency tables, hull convexity: all on the device (tn_faces.cu) ----
+    FaceTables ft;
     {
-        std::vector<float> hx((size_t)V * 3);
-        TN_CUDA(cudaMemcpyAsync(hx.data(), d_xyz, sizeof(float) * 3 * (size_t)V, cudaMemcpyDeviceToHost, s));
-        TN_CUDA(cudaStreamSynchronize(s));
-        walkable = !hull_tets.empty() && hull_is_convex_host(hx, tri, tt, hc);
+        int extra = 0;
+        const int rc = build_faces_device(d_xyz, V, d_cells, T, s, ft, &extra);
+        if (rc != TN_OK) return rc;
+        h->launches += extra;
     }
-    const uint32_t H = (uint32_t)hull_tets.size();
-
-    uint4 *d_tet_faces = nullptr;
-    uint4 *d_nbr = nullptr;
-    uint32_t *d_wind = nullptr, *d_hull_list = nullptr;
+    const uint32_t F = ft.F, H = ft.H;
+    const bool walkable = ft.walkable;
+    m.tri = reinterpret_cast<uint32_t *>(ft.tri); m.tt = reinterpret_cast<uint32_t *>(ft.tt);  // owned by the mesh from here on (free_mesh)
+    uint4 *d_tet_faces = ft.tet_faces;
+    uint4 *d_nbr = ft.nbr;
+    uint32_t *d_wind = ft.wind, *d_hull_list = ft.hull_list;
     uint32_t *keys = nullptr, *keys2 = nullptr, *vals = nullptr;
     int *bounds = nullptr;
     void *tmp = nullptr;
@@ -337,13 +199,6 @@ int build_mesh(tn_tracer *h, const float *d_xyz, uint32_t V, const uint32_t *d_c
             return fail(TN_ERR_CUDA, std::string(#expr) + " failed: " + cudaGetErrorString(_e)); \
         }                                                                                    \
     } while (0)
-
-    TN_CUDA_B(cudaMalloc(&m.tri, sizeof(uint4) * (size_t)F));
-    TN_CUDA_B(cudaMalloc(&m.tt, sizeof(uint2) * (size_t)F));
-    TN_CUDA_B(cudaMalloc(&d_tet_faces, sizeof(uint4) * (size_t)T));
-    TN_CUDA_B(cudaMemcpyAsync(m.tri, tri.data(), sizeof(uint4) * (size_t)F, cudaMemcpyHostToDevice, s));
-    TN_CUDA_B(cudaMemcpyAsync(m.tt, tt.data(), sizeof(uint2) * (size_t)F, cudaMemcpyHostToDevice, s));
-    TN_CUDA_B(cudaMemcpyAsync(d_tet_faces, tet_faces.data(), sizeof(uint4) * (size_t)T, cudaMemcpyHostToDevice, s));
 
     // ---- levels ----
     BvhLevels lv{};
@@ -391,12 +246,6 @@ int build_mesh(tn_tracer *h, const float *d_xyz, uint32_t V, const uint32_t *d_c
     // ---- adjacency walk: per-tetrahedron records + a small BVH over the tetrahedra that own a hull face ----
     BvhLevels hlv{};
     if (walkable) {
-        TN_CUDA_B(cudaMalloc(&d_nbr, sizeof(uint4) * (size_t)T));
-        TN_CUDA_B(cudaMalloc(&d_wind, sizeof(uint32_t) * (size_t)T));
-        TN_CUDA_B(cudaMalloc(&d_hull_list, sizeof(uint32_t) * (size_t)H));
-        TN_CUDA_B(cudaMemcpyAsync(d_nbr, nbr.data(), sizeof(uint4) * (size_t)T, cudaMemcpyHostToDevice, s));
-        TN_CUDA_B(cudaMemcpyAsync(d_wind, wind.data(), sizeof(uint32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
-        TN_CUDA_B(cudaMemcpyAsync(d_hull_list, hull_tets.data(), sizeof(uint32_t) * (size_t)H, cudaMemcpyHostToDevice, s));
         TN_CUDA_B(cudaMalloc(&m.walk, sizeof(WalkRec) * (size_t)T));
         k_walk_records<<<(T + 127) / 128, 128, 0, s>>>(d_xyz, (const uint4 *)d_cells, d_tet_faces, d_nbr, d_wind, T, m.walk);
         uint32_t hc_ = H, hoff = 0;

@@ -106,6 +106,18 @@ struct tn_tracer {
 
 namespace tn {
 int build_mesh(tn_tracer *h, const float *d_xyz, uint32_t V, const uint32_t *d_cells, uint32_t T, cudaStream_t s);
+// device-built face / adjacency tables (tn_faces.cu); all pointers are device allocations handed to the caller
+struct FaceTables {
+    uint4 *tri = nullptr;        // [F] stored winding (reference numbering), padded
+    uint2 *tt = nullptr;         // [F] (first owner, second owner or TN_EMPTY)
+    uint4 *tet_faces = nullptr;  // [T] face id | TN_FACE_OWNER | TN_FACE_HULL of the face opposite local vertex j
+    uint4 *nbr = nullptr;        // [T] neighbour across each face
+    uint32_t *wind = nullptr;    // [T] stored windings as local vertex indices (2 bits x 3 x 4)
+    uint32_t *hull_list = nullptr;  // [H] tetrahedra owning a hull face, ascending
+    uint32_t F = 0, H = 0;
+    bool walkable = false;       // the hull is a closed convex surface
+};
+int build_faces_device(const float *d_xyz, uint32_t V, const uint32_t *d_cells, uint32_t T, cudaStream_t s, FaceTables &out, int *launches);
 void free_mesh(tn_tracer *h);
 void free_render(tn_tracer *h);
 int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
