@@ -112,6 +112,12 @@ extern "C" int tn_set_walk_min_rays(tn_tracer *h, uint32_t n) {
     h->walk_min_rays = n;
     return TN_OK;
 }
+// batches below walk_min_rays and up to `n` rays take the one-ray-per-warp form of the walk (0 = never)
+extern "C" int tn_set_walk_solo_max_rays(tn_tracer *h, uint32_t n) {
+    if (!h) return tn::fail(TN_ERR_ARG, "null tracer");
+    h->walk_solo_max_rays = n;
+    return TN_OK;
+}
 static uint32_t g_last_exact = 0;
 extern "C" uint32_t tn_debug_last_exact_count(void) { return g_last_exact; }
 // test hook: (walkable mesh?, number of rays the last trace_rays call handed to the exact stage); synchronises the device

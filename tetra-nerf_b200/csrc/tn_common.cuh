@@ -99,7 +99,9 @@ struct tn_tracer {
     uint32_t ovf_cap = 0;
     unsigned long long *d_walk_keys = nullptr;  // [R, M] (t, face) keys written by the adjacency walk
     size_t walk_keys_cap = 0;
-    uint32_t walk_min_rays = 10240;  // batches at least this large take the adjacency-walk fast path (see launch_trace)
+    uint32_t walk_min_rays = 10240;  // batches at least this large take the thread-per-ray adjacency walk (see launch_trace)
+    uint32_t walk_solo_max_rays = 0;  // smaller batches up to this size take the one-ray-per-warp walk; 0 = off (default: it is
+                                      // issue-bound at ~300 instructions per step and measures 0.38 ms vs the gather's 0.29 ms at 4096 rays)
     uint64_t launches = 0;
     tn::RenderState *render = nullptr;
 };
@@ -121,7 +123,7 @@ int build_faces_device(const float *d_xyz, uint32_t V, const uint32_t *d_cells, 
 void free_mesh(tn_tracer *h);
 void free_render(tn_tracer *h);
 int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
-                float *dist, uint32_t *verts, unsigned long long *keys, uint32_t *list, uint32_t *list_count, cudaStream_t s);
+                float *dist, uint32_t *verts, unsigned long long *keys, uint32_t *list, uint32_t *list_count, bool solo, cudaStream_t s);
 int launch_tail_fill(tn_tracer *h, uint32_t R, uint32_t M, const uint32_t *num, uint32_t *cells, float *bary, float *dist, uint32_t *verts,
                      cudaStream_t s);
 int launch_prefetch(tn_tracer *h, const void *const *extra, const size_t *extra_bytes, int nextra, cudaStream_t s);

@@ -481,12 +481,15 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
         return TN_OK;
     };
     const uint32_t want = (R + TRACE_WARPS - 1) / TRACE_WARPS;
-    // path choice: the adjacency walk needs ~5x fewer instructions per ray but runs one thread per ray, so it only pays
-    // once there are enough rays to fill the machine; small batches are latency-bound and use the warp-per-ray gather.
-    // TETRANERF_B200_WALK=0/1 forces the choice (tests exercise both), default: walk when R >= walk_min_rays.
+    // path choice.  The adjacency walk needs ~40x fewer instructions per ray than the all-hits gather but is a serial chain
+    // of L2 round trips per ray: with >= walk_min_rays rays it runs 32 rays per warp (throughput); smaller batches up to
+    // walk_solo_max_rays run ONE ray per warp (latency: no divergence, no scattered 32-way accesses); anything else, and
+    // meshes that cannot be walked, take the warp-per-ray BVH gather.  TETRANERF_B200_WALK=0/1/2 forces BVH / 32-per-warp
+    // walk / solo walk (the tests exercise all three through the setters).
     static const int walk_env = [] { const char *e = getenv("TETRANERF_B200_WALK"); return e ? atoi(e) : -1; }();
-    const bool use_walk = walk_env >= 0 ? walk_env != 0 : R >= h->walk_min_rays;
-    if (mode == 0 && h->mesh.walkable && M >= 4 && use_walk) {
+    const bool thread_walk = walk_env >= 0 ? walk_env == 1 : R >= h->walk_min_rays;
+    const bool solo_walk = walk_env >= 0 ? walk_env == 2 : (!thread_walk && R <= h->walk_solo_max_rays);
+    if (mode == 0 && h->mesh.walkable && M >= 4 && (thread_walk || solo_walk)) {
         // fast path: adjacency walk (tn_walk.cu); rays it cannot certify are listed for the exact stage below
         const size_t need = (size_t)R * M;
         if (h->walk_keys_cap < need) {
@@ -503,7 +506,7 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
         }
         uint32_t *list_count = reinterpret_cast<uint32_t *>(h->d_flags + 2);
         TN_CUDA(cudaMemsetAsync(list_count, 0, 2 * sizeof(uint32_t), s));
-        int rc = launch_walk(h, o, d, R, M, num, cells, bary, dist, verts, h->d_walk_keys, h->d_ovf_list, list_count, s);
+        int rc = launch_walk(h, o, d, R, M, num, cells, bary, dist, verts, h->d_walk_keys, h->d_ovf_list, list_count, solo_walk && !thread_walk, s);
         if (rc) return rc;
         p.dense = 0;
         p.hcap = M + 128; p.scap = M > 512 ? 2 * M : 1024; p.lcap = M > 512 ? M / 2 : 320;

@@ -1,4 +1,9 @@
 // tn_walk.cu -- fast path of trace_rays: adjacency walk through the tetrahedral mesh, one thread per ray.
+// Two kernels with the same semantics: k_walk, 32 rays per warp (throughput: large batches), and k_walk_coop, ONE ray per
+// warp with a few cooperating lanes (latency: batches that fit the machine in one or two waves of 32 single-warp blocks
+// per SM -- 8 lanes test the 8 children of a hull-BVH node at once, 4 lanes shear the 4 vertices and test the candidate
+// exit faces at once, so a step is one L2/L1 round trip plus ~150 dependent instructions, with no lane divergence and no
+// 32-way scattered loads and stores).
 //
 // The reference gathers every face hit of a ray with an OptiX any-hit program, sorts them and pairs consecutive
 // faces (src/optix/optix_trace_rays.cu:268-331).  In a conforming mesh with a convex hull (every Delaunay
@@ -175,6 +180,162 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams p) {
     }
 }
 
+// ---- one ray per warp, cooperating lanes ------------------------------------------------------------------------------
+// Same outputs, classification and fallbacks as k_walk (it is the same algorithm): lanes 0..7 search the hull BVH (one
+// child / one hull tetrahedron each), then lanes 0..3 walk: lane j shears vertex j and tests the face opposite vertex j.
+__device__ __forceinline__ float sel4f(uint32_t k, float a, float b, float c, float d) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
+
+__global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
+    __shared__ uint32_t stack[8 * TN_MAX_LEVELS + 8];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t ray = blockIdx.x;
+    if (lane >= 8u || ray >= p.R) return;
+    constexpr uint32_t M8 = 0xFFu, M4 = 0xFu;
+    const float ox = p.o[3 * (size_t)ray], oy = p.o[3 * (size_t)ray + 1], oz = p.o[3 * (size_t)ray + 2];
+    const float dx = p.d[3 * (size_t)ray], dy = p.d[3 * (size_t)ray + 1], dz = p.d[3 * (size_t)ray + 2];
+    const RaySetup rs = ray_setup(ox, oy, oz, dx, dy, dz);
+    if (!rs.valid) { if (lane == 0) p.num[ray] = 0; return; }
+    const size_t row = (size_t)ray * p.M;
+
+    // ---- hull entry: closest hit over the hull faces (smallest (t, face id) key); lane c takes child c of the popped node ----
+    u64 best = ~0ull;
+    float bu = 0.f, bv = 0.f;
+    uint32_t btet = TN_EMPTY, bj = 0;
+    {
+        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+        const float pad = 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + p.absmax);
+        int sp = 0;
+        if (lane == 0) stack[0] = (uint32_t)(p.hlv.nlevels - 1) << 28;
+        sp = 1;
+        __syncwarp(M8);
+        while (sp) {
+            const uint32_t e = stack[--sp];
+            __syncwarp(M8);  // everyone has read the entry before it can be overwritten
+            const uint32_t cl = (e >> 28) - 1u, cbase = (e & 0x0FFFFFFFu) << TN_FAN_LOG2;
+            const uint32_t nc = min(TN_FAN, p.hlv.count[cl] - cbase);
+            bool hit = false;
+            if (lane < nc) {
+                const float4 *np = p.hull_nodes + 2 * (size_t)(p.hlv.offset[cl] + cbase + lane);
+                hit = slab(__ldg(np), __ldg(np + 1), ox, oy, oz, ix, iy, iz, pad);
+            }
+            if (cl != 0) {
+                const uint32_t hm = __ballot_sync(M8, hit);
+                if (hit) stack[sp + __popc(hm & ((1u << lane) - 1u))] = (cl << 28) | (cbase + lane);
+                sp += __popc(hm);
+                __syncwarp(M8);
+                continue;
+            }
+            if (hit) {  // a hull tetrahedron: its hull faces are owned, their stored winding is this rotation
+                const float4 *lp = reinterpret_cast<const float4 *>(p.hull_leaves + cbase + lane);
+                const float4 v0 = __ldg(lp), v1 = __ldg(lp + 1), v2 = __ldg(lp + 2), v3 = __ldg(lp + 3);
+                const uint32_t f[4] = {__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w), __float_as_uint(v3.w)};
+                const Sheared s[4] = {shear(rs, v0.x, v0.y, v0.z), shear(rs, v1.x, v1.y, v1.z), shear(rs, v2.x, v2.y, v2.z), shear(rs, v3.x, v3.y, v3.z)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!(f[j] & TN_FACE_HULL)) continue;
+                    float t, u, v;
+                    if (tri_test(s[(j + 1) & 3], s[(j + 2) & 3], s[(j + 3) & 3], t, u, v)) {
+                        const u64 k = ((u64)__float_as_uint(t) << 32) | (f[j] & TN_FACE_MASK);
+                        if (k < best) { best = k; bu = u; bv = v; btet = p.hull_tet[cbase + lane]; bj = (uint32_t)j; }
+                    }
+                }
+            }
+        }
+        // the smallest key over the 8 lanes wins (keys are unique: a face is tested by one lane only)
+        u64 m = best;
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) {
+            const u64 other = __shfl_xor_sync(M8, m, o);
+            m = other < m ? other : m;
+        }
+        const uint32_t win = __ffs(__ballot_sync(M8, best == m)) - 1u;
+        best = m;
+        bu = __shfl_sync(M8, bu, win); bv = __shfl_sync(M8, bv, win);
+        btet = __shfl_sync(M8, btet, win); bj = __shfl_sync(M8, bj, win);
+    }
+    if (lane >= 4u) return;
+    if (btet == TN_EMPTY) { if (lane == 0) p.num[ray] = 0; return; }  // the ray misses the mesh
+
+    // ---- walk: lane j owns vertex j / the face opposite to it; every lane keeps the (uniform) bookkeeping ----
+    uint32_t c = btet, jin = bj, fin = (uint32_t)best, nfaces = 1, nrec = 0;
+    float t_in = __uint_as_float((uint32_t)(best >> 32)), u_in = bu, v_in = bv;
+    bool generic = true, exact = false, prev_small = false;
+    if (lane == 0) p.keys[row] = best;
+    for (;;) {
+        const float4 *wp = reinterpret_cast<const float4 *>(p.walk + c);
+        const float4 vj = __ldg(wp + lane);                 // vertex `lane` + the face id opposite to it
+        const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(wp + 4));
+        const uint4 vid = __ldg(reinterpret_cast<const uint4 *>(wp + 5));
+        const uint32_t wind = __ldg(reinterpret_cast<const uint32_t *>(wp + 6));
+        // the next record is one of the neighbours: start fetching them while this tetrahedron is intersected
+        const uint32_t nbj = sel4u(lane, nb.x, nb.y, nb.z, nb.w);
+        if (nbj != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nbj));
+        const uint32_t fwj = __float_as_uint(vj.w);
+        const uint32_t inm = __ballot_sync(M4, (fwj & TN_FACE_MASK) == fin);  // entry face (the face shared with the previous tetrahedron)
+        jin = inm ? (uint32_t)__ffs(inm) - 1u : 3u;
+        const Sheared sj = shear(rs, vj.x, vj.y, vj.z);
+        const uint32_t w = (wind >> (6 * lane)) & 63u;       // stored winding of my face as local vertex indices
+        const uint32_t a = w & 3u, b = (w >> 2) & 3u, cc = (w >> 4) & 3u;
+        Sheared A, B, Cv;
+        A.x = __shfl_sync(M4, sj.x, a); A.y = __shfl_sync(M4, sj.y, a); A.z = __shfl_sync(M4, sj.z, a);
+        B.x = __shfl_sync(M4, sj.x, b); B.y = __shfl_sync(M4, sj.y, b); B.z = __shfl_sync(M4, sj.z, b);
+        Cv.x = __shfl_sync(M4, sj.x, cc); Cv.y = __shfl_sync(M4, sj.y, cc); Cv.z = __shfl_sync(M4, sj.z, cc);
+        float t = 0.f, u = 0.f, v = 0.f;
+        const bool hit = lane != jin && tri_test(A, B, Cv, t, u, v);
+        const uint32_t hm = __ballot_sync(M4, hit);
+        if (__popc(hm) != 1) { exact = true; break; }
+        const uint32_t jout = (uint32_t)__ffs(hm) - 1u;
+        const float t_out = __shfl_sync(M4, t, jout), u_out = __shfl_sync(M4, u, jout), v_out = __shfl_sync(M4, v, jout);
+        const uint32_t fout = __shfl_sync(M4, fwj, jout) & TN_FACE_MASK;
+        // isolated sub-eps crossings: see k_walk
+        const bool small = fabsf(__fsub_rn(t_out, t_in)) < TN_EPS;
+        if (!(t_out > t_in) || (small && prev_small)) generic = false;
+        prev_small = small;
+        if (generic && !small) {
+            // record (optix_trace_rays.cu:216-225 with combine_indices :39-75), expressed in local vertex indices
+            const uint32_t wi = (wind >> (6 * jin)) & 63u, wo = (wind >> (6 * jout)) & 63u;
+            const uint32_t ia[3] = {wi & 3u, (wi >> 2) & 3u, (wi >> 4) & 3u}, oa[3] = {wo & 3u, (wo >> 2) & 3u, (wo >> 4) & 3u};
+            const float r2[3] = {__fsub_rn(__fsub_rn(1.0f, u_out), v_out), u_out, v_out};
+            float o2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (ia[q] == oa[i]) o2[q] = r2[i];
+            const size_t g = row + nrec;
+            if (lane == 0) {
+                p.cells[g] = c;
+                reinterpret_cast<float2 *>(p.dist)[g] = make_float2(t_in, t_out);
+            } else if (lane == 1) {
+                reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(sel4u(jin, vid.x, vid.y, vid.z, vid.w), sel4u(ia[0], vid.x, vid.y, vid.z, vid.w),
+                                                                   sel4u(ia[1], vid.x, vid.y, vid.z, vid.w), sel4u(ia[2], vid.x, vid.y, vid.z, vid.w));
+            } else if (lane == 2) {
+                float2 *bp = reinterpret_cast<float2 *>(p.bary + 6 * g);
+                bp[0] = make_float2(__fsub_rn(__fsub_rn(1.0f, u_in), v_in), u_in);
+                bp[1] = make_float2(v_in, o2[0]);
+                bp[2] = make_float2(o2[1], o2[2]);
+            }
+            nrec++;
+        }
+        if (lane == 3) p.keys[row + nfaces] = ((u64)__float_as_uint(t_out) << 32) | fout;
+        nfaces++;
+        const uint32_t next = sel4u(jout, nb.x, nb.y, nb.z, nb.w);
+        if (next == TN_EMPTY || nfaces >= p.M - 1) break;  // left the mesh, or the M-1 nearest faces are in (optix_trace_rays.cu:312-315)
+        c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out;
+    }
+    if (lane != 0) return;
+    if (exact) {
+        p.list[atomicAdd(p.list_count, 1u)] = ray;
+        atomicAdd(p.list_count + 1, 1u);  // diagnostics: rays that need the all-hits gather
+        p.num[ray] = 0;
+    } else if (!generic) {
+        p.list[atomicAdd(p.list_count, 1u)] = ray | 0x80000000u;
+        p.num[ray] = nfaces;  // number of keys; the pairing stage replaces it by the number of records
+    } else {
+        p.num[ray] = nrec;
+    }
+}
+
 // dense API tails (optix_trace_rays.cu:260-265 + the zeroed scratch tails pinned by the oracle): one warp per ray
 __global__ void k_tail_fill(uint32_t R, uint32_t M, const uint32_t *__restrict__ num, uint32_t *__restrict__ cells, float *__restrict__ bary,
                             float *__restrict__ dist, uint32_t *__restrict__ verts) {
@@ -193,12 +354,13 @@ __global__ void k_tail_fill(uint32_t R, uint32_t M, const uint32_t *__restrict__
 }
 
 int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
-                float *dist, uint32_t *verts, u64 *keys, uint32_t *list, uint32_t *list_count, cudaStream_t s) {
+                float *dist, uint32_t *verts, u64 *keys, uint32_t *list, uint32_t *list_count, bool solo, cudaStream_t s) {
     WalkParams p{};
     p.o = o; p.d = d; p.R = R; p.M = M; p.num = num; p.cells = cells; p.bary = bary; p.dist = dist; p.verts = verts;
     p.walk = h->mesh.walk; p.hull_nodes = h->mesh.hull_nodes; p.hull_leaves = h->mesh.hull_leaves; p.hull_tet = h->mesh.hull_tet;
     p.hlv = h->mesh.hull_lv; p.absmax = h->mesh.absmax; p.keys = keys; p.list = list; p.list_count = list_count;
-    k_walk<<<(R + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(p);
+    if (solo) k_walk_coop<<<R, 32, 0, s>>>(p);
+    else k_walk<<<(R + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(p);
     h->launches += 1;
     TN_CUDA(cudaGetLastError());
     return TN_OK;
