@@ -124,6 +124,15 @@ int tn_debug_trace_stats(tn_tracer *h, uint32_t *out2);
 int tn_render_debug_buffers(tn_tracer *h, void **ptrs16);
 /* one 128x128 tile out = A[128,K] * W[128,K]^T through the tcgen05 bf16x3 path; K in {64,128}; synchronous */
 int tn_debug_gemm_bf16x3(int device, const float *d_A, const float *d_W, uint32_t K, float *d_out, void *stream);
+/* microbenchmark behind tools/mma_rate.py: cycles for nrep x 8 tcgen05.mma (M128 N128 K16 bf16); mode bit 0: two accumulators,
+ * bit 1: A from shared memory instead of TMEM, bit 2: concurrent tcgen05.ld/st traffic; h_out2 = {issue cycles, issue+drain} */
+int tn_debug_mma_rate(int device, int nrep, int mode, uint32_t boff, long long *h_out2);
+/* in-kernel timeline of the NEXT fine-pass k_mlp launches (tools/mlp_timeline.py): device buffer of >= 65001 u64, first word
+ * zeroed by the caller; [1..n] = (tag << 40 | clock) records of CTA 0, [1000 + 8 b ..] per-CTA start/end/smid/tile counts.
+ * NULL switches it off. */
+int tn_debug_set_timeline(void *d_buf);
+/* rays of the last tn_debug_trace_stats call that needed the all-hits gather (subset of out2[1]) */
+uint32_t tn_debug_last_exact_count(void);
 
 /* number of kernels launched by this library on this tracer since creation (bench "gpu_launches") */
 uint64_t tn_launch_count(tn_tracer *h);

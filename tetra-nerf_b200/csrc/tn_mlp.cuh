@@ -228,7 +228,7 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
     constexpr uint32_t L = FINE ? 4 : 3;
     constexpr uint32_t NBUF = FINE ? 1 : 2;
     constexpr uint32_t idesc = make_idesc_bf16(128, 128);
-    mbar_wait_backoff_a(s.bars + 8u * (MLP_BAR_A_READY + SLOT), par, 32);
+    mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY + SLOT), par);
     par ^= 1u;
     const uint32_t l = layer;
     layer = l + 1u == L ? 0u : l + 1u;
@@ -239,7 +239,7 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         uint32_t tile = MLP_NO_TILE;
         const uint32_t b = NBUF == 2 ? (s.nseq & 1u) : 0u;
         if (!s.done) {
-            mbar_wait_backoff_a(s.bars + 8u * (MLP_BAR_A0_FULL + b), (s.nseq / NBUF) & 1u, 32);
+            mbar_wait_a(s.bars + 8u * (MLP_BAR_A0_FULL + b), (s.nseq / NBUF) & 1u);
             asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tile) : "r"(s.bars + MLP_TILE_IDS_OFF + 4u * (s.nseq & 7u)) : "memory");
             s.nseq++;
         }
