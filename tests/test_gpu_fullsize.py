@@ -72,15 +72,15 @@ def test_full_size_permutation_invariance_and_determinism(scene):
         assert np.array_equal(out2[k].cpu().numpy(), out[k][perm]), k
     # the other implementations of trace_rays give the same bits at full size: adjacency walk with 32 rays per warp
     # (walk_min_rays = 0) and with one ray per warp (solo); the default for 4096 rays is the warp-per-ray BVH gather
-    for min_rays, solo_max, is_walk in ((0, 0, True), (2**32 - 1, 2**32 - 1, True)):
-        tr.set_walk_min_rays(min_rays); tr.set_walk_solo_max_rays(solo_max)
+    for min_rays, solo, is_walk in ((0, (1, 0), True), (2**32 - 1, (0, 2**32 - 1), True)):
+        tr.set_walk_min_rays(min_rays); tr.set_walk_solo_range(*solo)
         out3 = tr.trace_rays(torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), 512)
         tr.synchronize()
         walkable, listed = tr.trace_stats()
         assert walkable and (not is_walk or listed < 0.15 * len(o))
         for k in KEYS:
             assert np.array_equal(out3[k].cpu().numpy(), out[k]), k
-    tr.set_walk_min_rays(10240); tr.set_walk_solo_max_rays(0)
+    tr.set_walk_min_rays(10240); tr.set_walk_solo_range(6144, 2**32 - 1)
 
 
 def test_full_size_render(scene):

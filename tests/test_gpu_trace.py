@@ -12,7 +12,7 @@ DEV = torch.device("cuda:0")
 KEYS = ["num_visited_cells", "visited_cells", "vertex_indices", "hit_distances", "barycentric_coordinates"]
 
 
-WALK = (0, 0)  # set by the autouse fixture: (walk_min_rays, walk_solo_max_rays)
+WALK = (0, 1, 0)  # set by the autouse fixture: (walk_min_rays, solo range lo, hi)
 
 
 @pytest.fixture(autouse=True, params=["walk", "walk_solo", "bvh"])
@@ -20,7 +20,7 @@ def trace_impl(request):
     """every test of this file runs against all three (bit-identical) implementations of trace_rays: adjacency walk with
     32 rays per warp, adjacency walk with one ray per warp, warp-per-ray BVH gather"""
     global WALK
-    WALK = {"walk": (0, 0), "walk_solo": (2**32 - 1, 2**32 - 1), "bvh": (2**32 - 1, 0)}[request.param]
+    WALK = {"walk": (0, 1, 0), "walk_solo": (2**32 - 1, 0, 2**32 - 1), "bvh": (2**32 - 1, 1, 0)}[request.param]
     yield request.param
 
 
@@ -30,7 +30,7 @@ def make_tracer(V, C):
     tr = cpp.TetrahedraTracer(DEV)
     tr.load_tetrahedra(torch.from_numpy(V).to(DEV), torch.from_numpy(C).to(DEV))
     tr.set_walk_min_rays(WALK[0])
-    tr.set_walk_solo_max_rays(WALK[1])
+    tr.set_walk_solo_range(WALK[1], WALK[2])
     return tr
 
 
@@ -249,7 +249,7 @@ def test_walk_fast_path_classification(small_mesh):
     g = gpu_trace(tr, o, d, 512)
     walkable, listed = tr.trace_stats()
     assert walkable
-    if WALK[0] == 0 or WALK[1] != 0:  # either form of the walk
+    if WALK[0] == 0 or WALK[1] <= WALK[2]:  # either form of the walk
         assert 0 < listed < 0.15 * len(o), listed
     assert_same(g, orc.OracleMesh(V, C).trace_rays(o, d, 512))
 

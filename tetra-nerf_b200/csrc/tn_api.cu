@@ -112,10 +112,11 @@ extern "C" int tn_set_walk_min_rays(tn_tracer *h, uint32_t n) {
     h->walk_min_rays = n;
     return TN_OK;
 }
-// batches below walk_min_rays and up to `n` rays take the one-ray-per-warp form of the walk (0 = never)
-extern "C" int tn_set_walk_solo_max_rays(tn_tracer *h, uint32_t n) {
+// batches below walk_min_rays with lo <= rays <= hi take the one-ray-per-warp form of the walk (lo > hi = never)
+extern "C" int tn_set_walk_solo_range(tn_tracer *h, uint32_t lo, uint32_t hi) {
     if (!h) return tn::fail(TN_ERR_ARG, "null tracer");
-    h->walk_solo_max_rays = n;
+    h->walk_solo_min_rays = lo;
+    h->walk_solo_max_rays = hi;
     return TN_OK;
 }
 static uint32_t g_last_exact = 0;

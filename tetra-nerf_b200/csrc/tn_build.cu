@@ -115,9 +115,32 @@ __global__ void k_walk_records(const float *__restrict__ xyz, const uint4 *__res
         r.v[k] = make_float4(xyz[3 * (size_t)id[k]], xyz[3 * (size_t)id[k] + 1], xyz[3 * (size_t)id[k] + 2], __uint_as_float(fi[k]));
     r.nbr[0] = nb.x; r.nbr[1] = nb.y; r.nbr[2] = nb.z; r.nbr[3] = nb.w;
     r.vid[0] = c.x; r.vid[1] = c.y; r.vid[2] = c.z; r.vid[3] = c.w;
-    r.wind = wind[i];
+    const uint32_t w = wind[i];
+    r.wind = w;
+    uint32_t perm = 0;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) r.pad[k] = 0;
+    for (uint32_t jin = 0; jin < 4; ++jin) {
+        const uint32_t wi = (w >> (6 * jin)) & 63u;
+        const uint32_t ia[3] = {wi & 3u, (wi >> 2) & 3u, (wi >> 4) & 3u};
+        perm |= (jin | (ia[0] << 2) | (ia[1] << 4) | (ia[2] << 6)) << (8 * jin);
+        uint32_t m = 0;
+#pragma unroll
+        for (uint32_t jout = 0; jout < 4; ++jout) {
+            const uint32_t wo = (w >> (6 * jout)) & 63u;
+            const uint32_t oa[3] = {wo & 3u, (wo >> 2) & 3u, (wo >> 4) & 3u};
+#pragma unroll
+            for (uint32_t q = 0; q < 3; ++q) {
+                uint32_t code = 3u;  // entry-face vertex q is not on the exit face
+#pragma unroll
+                for (uint32_t k = 0; k < 3; ++k)
+                    if (ia[q] == oa[k]) code = k;
+                m |= code << (6 * jout + 2 * q);
+            }
+        }
+        r.map[jin] = m;
+    }
+    r.perm = perm;
+    r.pad[0] = r.pad[1] = 0;
     out[i] = r;
 }
 

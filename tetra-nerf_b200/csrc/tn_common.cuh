@@ -62,9 +62,13 @@ struct WalkRec {
     float4 v[4];       // as LeafRec
     uint32_t nbr[4];   // tetrahedron across face j (TN_EMPTY on the hull)
     uint32_t vid[4];   // the cell's vertex ids
+    uint32_t map[4];   // map[jin]: for each exit face jout 6 bits = three 2-bit codes: which exit barycentric (0: 1-u-v, 1: u, 2: v,
+                       // 3: none -> 0) belongs to slot q of the ENTRY face's winding (combine_indices, optix_trace_rays.cu:39-75)
     uint32_t wind;     // 4 x 6 bits: stored winding of face j as three local vertex indices (2 bits each, a | b<<2 | c<<4)
-    uint32_t pad[7];
+    uint32_t perm;     // 4 x 8 bits: record vertex order when entering through face jin: (jin, wind[jin].a, .b, .c) as local indices
+    uint32_t pad[2];
 };
+static_assert(sizeof(WalkRec) == 128, "WalkRec is one 128-byte line");
 
 struct Mesh {
     const float *xyz = nullptr;      // borrowed, [V,3]
@@ -100,8 +104,9 @@ struct tn_tracer {
     unsigned long long *d_walk_keys = nullptr;  // [R, M] (t, face) keys written by the adjacency walk
     size_t walk_keys_cap = 0;
     uint32_t walk_min_rays = 10240;  // batches at least this large take the thread-per-ray adjacency walk (see launch_trace)
-    uint32_t walk_solo_max_rays = 0;  // smaller batches up to this size take the one-ray-per-warp walk; 0 = off (default: it is
-                                      // issue-bound at ~300 instructions per step and measures 0.38 ms vs the gather's 0.29 ms at 4096 rays)
+    // batches of [walk_solo_min_rays, walk_solo_max_rays] rays (below walk_min_rays) take the one-ray-per-warp walk: measured
+    // (profiles/r1_trace_sweep.json) 0.32 / 0.51 ms at 4096 / 8192 rays against the gather's 0.29 / 0.56 ms
+    uint32_t walk_solo_min_rays = 6144, walk_solo_max_rays = 0xFFFFFFFFu;
     uint64_t launches = 0;
     tn::RenderState *render = nullptr;
 };

@@ -488,7 +488,7 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
     // walk / solo walk (the tests exercise all three through the setters).
     static const int walk_env = [] { const char *e = getenv("TETRANERF_B200_WALK"); return e ? atoi(e) : -1; }();
     const bool thread_walk = walk_env >= 0 ? walk_env == 1 : R >= h->walk_min_rays;
-    const bool solo_walk = walk_env >= 0 ? walk_env == 2 : (!thread_walk && R <= h->walk_solo_max_rays);
+    const bool solo_walk = walk_env >= 0 ? walk_env == 2 : (!thread_walk && R >= h->walk_solo_min_rays && R <= h->walk_solo_max_rays);
     if (mode == 0 && h->mesh.walkable && M >= 4 && (thread_walk || solo_walk)) {
         // fast path: adjacency walk (tn_walk.cu); rays it cannot certify are listed for the exact stage below
         const size_t need = (size_t)R * M;

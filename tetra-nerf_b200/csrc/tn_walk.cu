@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams p) {
         const float4 v0 = __ldg(wp), v1 = __ldg(wp + 1), v2 = __ldg(wp + 2), v3 = __ldg(wp + 3);
         const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(wp + 4));
         const uint4 vid = __ldg(reinterpret_cast<const uint4 *>(wp + 5));
-        const uint32_t wind = __ldg(reinterpret_cast<const uint32_t *>(wp + 6));
+        const uint4 map = __ldg(reinterpret_cast<const uint4 *>(wp + 6));
+        const uint2 wp2 = __ldg(reinterpret_cast<const uint2 *>(wp + 7));
+        const uint32_t wind = wp2.x, perm = wp2.y;
         // the next record is one of the neighbours: start fetching all of them while this tetrahedron is intersected
         if (nb.x != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nb.x));
         if (nb.y != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nb.y));
@@ -142,19 +144,19 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams p) {
         prev_small = small;
         if (generic && !small) {
             // record (optix_trace_rays.cu:216-225 with combine_indices :39-75), expressed in local vertex indices
-            const uint32_t wi = (wind >> (6 * jin)) & 63u, wo = (wind >> (6 * jout)) & 63u;
-            const uint32_t ia[3] = {wi & 3u, (wi >> 2) & 3u, (wi >> 4) & 3u}, oa[3] = {wo & 3u, (wo >> 2) & 3u, (wo >> 4) & 3u};
-            const float r2[3] = {__fsub_rn(__fsub_rn(1.0f, u_out), v_out), u_out, v_out};
-            float o2[3] = {0.f, 0.f, 0.f};
+            // (the vertex order and the slot of every exit barycentric come from the tables built with the record)
+            const uint32_t pm = perm >> (8 * jin), mc = sel4u(jin, map.x, map.y, map.z, map.w) >> (6 * jout);
+            const float r0 = __fsub_rn(__fsub_rn(1.0f, u_out), v_out);
+            float o2[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    if (ia[q] == oa[i]) o2[q] = r2[i];
+            for (int q = 0; q < 3; ++q) {
+                const uint32_t code = (mc >> (2 * q)) & 3u;
+                o2[q] = code == 0 ? r0 : (code == 1 ? u_out : (code == 2 ? v_out : 0.f));
+            }
             const size_t g = row + nrec;
             p.cells[g] = c;
-            reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(sel4u(jin, vid.x, vid.y, vid.z, vid.w), sel4u(ia[0], vid.x, vid.y, vid.z, vid.w),
-                                                               sel4u(ia[1], vid.x, vid.y, vid.z, vid.w), sel4u(ia[2], vid.x, vid.y, vid.z, vid.w));
+            reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(sel4u(pm & 3u, vid.x, vid.y, vid.z, vid.w), sel4u((pm >> 2) & 3u, vid.x, vid.y, vid.z, vid.w),
+                                                               sel4u((pm >> 4) & 3u, vid.x, vid.y, vid.z, vid.w), sel4u((pm >> 6) & 3u, vid.x, vid.y, vid.z, vid.w));
             float2 *bp = reinterpret_cast<float2 *>(p.bary + 6 * g);
             bp[0] = make_float2(__fsub_rn(__fsub_rn(1.0f, u_in), v_in), u_in);
             bp[1] = make_float2(v_in, o2[0]);
@@ -263,12 +265,13 @@ __global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
     if (lane == 0) p.keys[row] = best;
     for (;;) {
         const float4 *wp = reinterpret_cast<const float4 *>(p.walk + c);
-        const float4 vj = __ldg(wp + lane);                 // vertex `lane` + the face id opposite to it
-        const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(wp + 4));
-        const uint4 vid = __ldg(reinterpret_cast<const uint4 *>(wp + 5));
-        const uint32_t wind = __ldg(reinterpret_cast<const uint32_t *>(wp + 6));
+        const uint32_t *wq = reinterpret_cast<const uint32_t *>(wp);
+        const float4 vj = __ldg(wp + lane);                       // vertex `lane` + the face id opposite to it
+        const uint32_t nbj = __ldg(wq + 16 + lane);               // neighbour across my face
+        const uint32_t vidj = __ldg(wq + 20 + lane);              // my vertex id
+        const uint2 wp2 = __ldg(reinterpret_cast<const uint2 *>(wp + 7));
+        const uint32_t wind = wp2.x, perm = wp2.y;
         // the next record is one of the neighbours: start fetching them while this tetrahedron is intersected
-        const uint32_t nbj = sel4u(lane, nb.x, nb.y, nb.z, nb.w);
         if (nbj != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nbj));
         const uint32_t fwj = __float_as_uint(vj.w);
         const uint32_t inm = __ballot_sync(M4, (fwj & TN_FACE_MASK) == fin);  // entry face (the face shared with the previous tetrahedron)
@@ -287,39 +290,34 @@ __global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
         const uint32_t jout = (uint32_t)__ffs(hm) - 1u;
         const float t_out = __shfl_sync(M4, t, jout), u_out = __shfl_sync(M4, u, jout), v_out = __shfl_sync(M4, v, jout);
         const uint32_t fout = __shfl_sync(M4, fwj, jout) & TN_FACE_MASK;
+        const uint32_t next = __shfl_sync(M4, nbj, jout);
         // isolated sub-eps crossings: see k_walk
         const bool small = fabsf(__fsub_rn(t_out, t_in)) < TN_EPS;
         if (!(t_out > t_in) || (small && prev_small)) generic = false;
         prev_small = small;
+        // record (optix_trace_rays.cu:216-225 with combine_indices :39-75): lane q writes slot q of every field; the vertex
+        // order and the slot of every exit barycentric come from the tables built with the record
+        const uint32_t vq = __shfl_sync(M4, vidj, (perm >> (8 * jin + 2 * lane)) & 3u);
         if (generic && !small) {
-            // record (optix_trace_rays.cu:216-225 with combine_indices :39-75), expressed in local vertex indices
-            const uint32_t wi = (wind >> (6 * jin)) & 63u, wo = (wind >> (6 * jout)) & 63u;
-            const uint32_t ia[3] = {wi & 3u, (wi >> 2) & 3u, (wi >> 4) & 3u}, oa[3] = {wo & 3u, (wo >> 2) & 3u, (wo >> 4) & 3u};
-            const float r2[3] = {__fsub_rn(__fsub_rn(1.0f, u_out), v_out), u_out, v_out};
-            float o2[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    if (ia[q] == oa[i]) o2[q] = r2[i];
             const size_t g = row + nrec;
-            if (lane == 0) {
+            // branch-free per-lane values (selp): entry / exit barycentric of slot `lane`
+            const uint32_t code = (__ldg(wq + 24 + jin) >> (6 * jout + 2 * lane)) & 3u;  // map[jin]: same line, L1 hit
+            const float r0 = __fsub_rn(__fsub_rn(1.0f, u_out), v_out), e0 = __fsub_rn(__fsub_rn(1.0f, u_in), v_in);
+            const float ev = sel3((int)lane, e0, u_in, v_in);
+            float xv = sel3((int)code, r0, u_out, v_out);
+            xv = code == 3u ? 0.f : xv;
+            p.verts[4 * g + lane] = vq;
+            if (lane < 3u) {
+                p.bary[6 * g + lane] = ev;
+                p.bary[6 * g + 3 + lane] = xv;
+            } else {
                 p.cells[g] = c;
                 reinterpret_cast<float2 *>(p.dist)[g] = make_float2(t_in, t_out);
-            } else if (lane == 1) {
-                reinterpret_cast<uint4 *>(p.verts)[g] = make_uint4(sel4u(jin, vid.x, vid.y, vid.z, vid.w), sel4u(ia[0], vid.x, vid.y, vid.z, vid.w),
-                                                                   sel4u(ia[1], vid.x, vid.y, vid.z, vid.w), sel4u(ia[2], vid.x, vid.y, vid.z, vid.w));
-            } else if (lane == 2) {
-                float2 *bp = reinterpret_cast<float2 *>(p.bary + 6 * g);
-                bp[0] = make_float2(__fsub_rn(__fsub_rn(1.0f, u_in), v_in), u_in);
-                bp[1] = make_float2(v_in, o2[0]);
-                bp[2] = make_float2(o2[1], o2[2]);
             }
             nrec++;
         }
-        if (lane == 3) p.keys[row + nfaces] = ((u64)__float_as_uint(t_out) << 32) | fout;
+        if (lane == 0) p.keys[row + nfaces] = ((u64)__float_as_uint(t_out) << 32) | fout;
         nfaces++;
-        const uint32_t next = sel4u(jout, nb.x, nb.y, nb.z, nb.w);
         if (next == TN_EMPTY || nfaces >= p.M - 1) break;  // left the mesh, or the M-1 nearest faces are in (optix_trace_rays.cu:312-315)
         c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out;
     }

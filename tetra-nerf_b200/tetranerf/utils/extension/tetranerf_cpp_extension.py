@@ -36,7 +36,7 @@ _lib.tn_interpolate_values.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp
 _lib.tn_interpolate_values_backward.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]
 _lib.tn_debug_trace_stats.argtypes = [_vp, C.POINTER(_u32)]
 _lib.tn_set_walk_min_rays.argtypes = [_vp, _u32]
-_lib.tn_set_walk_solo_max_rays.argtypes = [_vp, _u32]
+_lib.tn_set_walk_solo_range.argtypes = [_vp, _u32, _u32]
 _lib.tn_launch_count.restype = C.c_uint64
 _lib.tn_launch_count.argtypes = [_vp]
 
@@ -141,9 +141,9 @@ class TetrahedraTracer:
         """batches of >= n rays use the adjacency-walk implementation of trace_rays (0 = always, 2**32-1 = never)"""
         _check(_lib.tn_set_walk_min_rays(self._h, int(n)))
 
-    def set_walk_solo_max_rays(self, n: int) -> None:
-        """batches below walk_min_rays and up to n rays use the one-ray-per-warp form of the walk (0 = never)"""
-        _check(_lib.tn_set_walk_solo_max_rays(self._h, int(n)))
+    def set_walk_solo_range(self, lo: int, hi: int) -> None:
+        """batches below walk_min_rays with lo <= rays <= hi use the one-ray-per-warp form of the walk (lo > hi = never)"""
+        _check(_lib.tn_set_walk_solo_range(self._h, int(lo), int(hi)))
 
     def trace_stats(self):
         """(walkable mesh?, rays of the last trace_rays that took the exact stage) -- test/diagnostic hook"""
