@@ -80,9 +80,11 @@ int tn_find_visited_cells(tn_tracer *h, uint32_t R, uint32_t S, uint32_t M, cons
 int tn_interpolate_values(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi, const float *d_w,
                           const float *d_field, float *d_out, float *d_scratch, void *stream);
 /* interpolate_values_backward<D> -- src/py_binding.cpp:341-372, src/tetrahedra_tracer.cu:223-248.
- *   d_grad_in f32[N,C], d_grad_field f32[C,V] (zeroed by this call, py_binding.cpp:360). */
+ *   d_grad_in f32[N,C], d_grad_field f32[C,V] (every element written by this call, py_binding.cpp:360).
+ *   d_scratch: NULL (scalar atomics straight into the feature-major gradient, as the reference), or >= C*V floats for
+ *   a row-major [V,C] accumulator filled with 16-byte vector reductions and transposed at the end (needs C % 4 == 0). */
 int tn_interpolate_values_backward(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi,
-                                   const float *d_w, const float *d_grad_in, float *d_grad_field, void *stream);
+                                   const float *d_w, const float *d_grad_in, float *d_grad_field, float *d_scratch, void *stream);
 
 /* ---- fused forward render (new; replaces model.py:531-662 between trace_rays and the pixel) -------
  * Weights are passed once (tn_render_set_weights) in nerfstudio state-dict layout and repacked on

@@ -146,9 +146,44 @@ static int interp_fwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t *vi, co
     }
     return TN_OK;
 }
+// The same sums accumulated into a row-major [V,C] shadow: lane l of a (sample, vertex) pair adds 4 consecutive features
+// with ONE 16-byte vector reduction (red.global.add.v4.f32, sm_90+), so a vertex row takes C/4 coalesced atomics instead of
+// C scalar ones spread over C different cache lines of the feature-major gradient.  The caller transposes the shadow.
+template <int D>
+__global__ void k_interp_bwd_rows(uint32_t N, uint32_t C4, const uint32_t *__restrict__ vi, const float *__restrict__ w,
+                                  const float4 *__restrict__ gin, float4 *__restrict__ grow) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (sample, 4-feature group)
+    if (idx >= (size_t)N * C4) return;
+    const uint32_t i = (uint32_t)(idx / C4), j = (uint32_t)(idx % C4);
+    const float4 g = __ldg(gin + idx);
+    float weight = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        // k < D-1: vertex k+1 with weight w[k]; k == D-1: vertex 0 with the remaining weight (tetrahedra_tracer.cu:231-247)
+        float wk;
+        uint32_t v;
+        if (k < D - 1) { wk = w[(size_t)i * (D - 1) + k]; v = vi[(size_t)i * D + k + 1]; weight = __fadd_rn(weight, wk); }
+        else { wk = __fsub_rn(1.0f, weight); v = vi[(size_t)i * D]; }
+        if (v == TN_EMPTY) continue;
+        float4 *dst = grow + (size_t)v * C4 + j;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__fmul_rn(wk, g.x)), "f"(__fmul_rn(wk, g.y)),
+                     "f"(__fmul_rn(wk, g.z)), "f"(__fmul_rn(wk, g.w))
+                     : "memory");
+    }
+}
+
 template <int D>
 static int interp_bwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t *vi, const float *w, const float *gin, float *gfield,
-                      cudaStream_t s) {
+                      float *scratch, cudaStream_t s) {
+    if (scratch && (C & 3u) == 0 && ((uintptr_t)gin & 15) == 0 && ((uintptr_t)scratch & 15) == 0) {
+        cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)C * V, s);
+        const size_t total = (size_t)N * (C / 4);
+        k_interp_bwd_rows<D><<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(N, C / 4, vi, w, (const float4 *)gin, (float4 *)scratch);
+        dim3 tb(32, 8), tg((C + 31) / 32, (V + 31) / 32);
+        k_transpose<<<tg, tb, 0, s>>>(scratch, gfield, V, C);  // [V,C] -> [C,V]
+        return TN_OK;
+    }
+    cudaMemsetAsync(gfield, 0, sizeof(float) * (size_t)C * V, s);  // py_binding.cpp:360
     const size_t total = (size_t)N * C;
     k_interp_bwd<D><<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(N, C, V, vi, w, gin, gfield);
     return TN_OK;
@@ -187,16 +222,18 @@ extern "C" int tn_interpolate_values(int device, uint32_t D, uint32_t N, uint32_
 }
 
 extern "C" int tn_interpolate_values_backward(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi,
-                                              const float *d_w, const float *d_grad_in, float *d_grad_field, void *stream) {
+                                              const float *d_w, const float *d_grad_in, float *d_grad_field, float *d_scratch, void *stream) {
     tn::DeviceGuard g(device);
     cudaStream_t s = (cudaStream_t)stream;
-    TN_CUDA(cudaMemsetAsync(d_grad_field, 0, sizeof(float) * (size_t)C * V, s));  // py_binding.cpp:360
-    if (N == 0 || C == 0) return TN_OK;
+    if (N == 0 || C == 0) {
+        TN_CUDA(cudaMemsetAsync(d_grad_field, 0, sizeof(float) * (size_t)C * V, s));  // py_binding.cpp:360
+        return TN_OK;
+    }
     switch (D) {  // py_binding.cpp:278-296
-        case 2: tn::interp_bwd<2>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, s); break;
-        case 3: tn::interp_bwd<3>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, s); break;
-        case 4: tn::interp_bwd<4>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, s); break;
-        case 6: tn::interp_bwd<6>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, s); break;
+        case 2: tn::interp_bwd<2>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
+        case 3: tn::interp_bwd<3>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
+        case 4: tn::interp_bwd<4>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
+        case 6: tn::interp_bwd<6>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
         default: return tn::fail(TN_ERR_ARG, "Unsupported interpolation dimension with value " + std::to_string(D));
     }
     TN_CUDA(cudaGetLastError());

@@ -33,7 +33,7 @@ _lib.tn_trace_rays_triangles.argtypes = [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _v
 _lib.tn_find_tetrahedra.argtypes = [_vp, _vp, _u32, _vp, _vp, _vp, _vp]
 _lib.tn_find_visited_cells.argtypes = [_vp, _u32, _u32, _u32] + [_vp] * 11
 _lib.tn_interpolate_values.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]
-_lib.tn_interpolate_values_backward.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]
+_lib.tn_interpolate_values_backward.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]
 _lib.tn_debug_trace_stats.argtypes = [_vp, C.POINTER(_u32)]
 _lib.tn_set_walk_min_rays.argtypes = [_vp, _u32]
 _lib.tn_set_walk_solo_range.argtypes = [_vp, _u32, _u32]
@@ -293,8 +293,12 @@ def interpolate_values_backward(vertex_indices, barycentric_coordinates, field, 
     _require(grad_in.size(-1) == Cdim, "grad_in must have shape [..., field_dim]")
     dev = grad_in.device
     grad_field = torch.empty((Cdim, V), dtype=torch.float32, device=dev)
+    grad_in = grad_in.contiguous()
+    # row-major [V,C] accumulator for the vector-reduction path (worth it once there is more than a handful of samples)
+    scratch = torch.empty((V, Cdim), dtype=torch.float32, device=dev) if (Cdim % 4 == 0 and N >= 1024) else None
     _check(_lib.tn_interpolate_values_backward(dev.index, D, N, Cdim, V, vertex_indices.data_ptr(), barycentric_coordinates.data_ptr(),
-                                               grad_in.data_ptr(), grad_field.data_ptr(), _stream(dev)))
+                                               grad_in.data_ptr(), grad_field.data_ptr(), scratch.data_ptr() if scratch is not None else None,
+                                               _stream(dev)))
     return grad_field
 
 
