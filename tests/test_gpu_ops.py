@@ -47,6 +47,39 @@ def test_find_visited_cells_vs_oracle(traced):
     assert 0.2 < ref["mask"].mean() < 0.95
 
 
+def test_find_visited_cells_arbitrary_segments():
+    """the matcher on hand-made segment lists, including NON-monotone t_out (the warp kernel's literal fallback), empty rays,
+    rays that fill M, NaN samples: bit-equal to the literal loop of the oracle (tetrahedra_tracer.cu:129-160)"""
+    from tetranerf import cpp
+
+    rng = np.random.default_rng(11)
+    R, M, S = 257, 64, 101
+    num = rng.integers(0, M + 1, R).astype(np.int32)
+    num[:4] = (0, 1, M, M)
+    t_in = np.sort(rng.uniform(0.5, 3.0, (R, M)).astype(np.float32), axis=1)
+    t_out = t_in + rng.uniform(0.0, 0.08, (R, M)).astype(np.float32)   # overlapping segments, t_out mostly increasing ...
+    bad = rng.random(R) < 0.5
+    t_out[bad] = rng.permutation(t_out[bad].T).T                        # ... and shuffled (non-monotone) on half of the rays
+    hd = np.stack([t_in, t_out], -1)
+    cells = rng.integers(0, 1000, (R, M)).astype(np.int32)
+    verts = rng.integers(0, 500, (R, M, 4)).astype(np.int32)
+    bary = rng.random((R, M, 2, 3)).astype(np.float32)
+    dist = rng.uniform(0.3, 3.3, (R, S)).astype(np.float32)
+    dist[::3] = np.sort(dist[::3], axis=1)
+    dist[5, 7] = np.nan
+    V, C = syn.delaunay_mesh(64, seed=1)
+    tr = cpp.TetrahedraTracer(DEV)
+    tr.load_tetrahedra(torch.from_numpy(V).to(DEV), torch.from_numpy(C).to(DEV))
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    g = tr.find_visited_cells(t(num), t(cells), t(bary), t(hd), t(verts), t(dist))
+    ref = orc.find_visited_cells(num, cells, bary, hd, verts, dist)
+    assert np.array_equal(g["mask"].cpu().numpy(), ref["mask"])
+    assert np.array_equal(g["cell_indices"].cpu().numpy(), ref["cell_indices"])
+    assert np.array_equal(g["vertex_indices"].cpu().numpy(), ref["vertex_indices"])
+    assert np.array_equal(g["barycentric_coordinates"].cpu().numpy().view(np.uint32), ref["barycentric_coordinates"].view(np.uint32))
+    assert ref["mask"].mean() > 0.05
+
+
 @pytest.mark.parametrize("D,Cdim", [(4, 64), (4, 7), (3, 16), (2, 5), (6, 32)])
 def test_interpolate_values_vs_oracle(traced, D, Cdim):
     from tetranerf import cpp

@@ -52,6 +52,91 @@ __global__ void k_match(uint32_t R, uint32_t S, uint32_t M, const uint32_t *__re
     }
 }
 
+// ---- find_matched_cells, one warp per ray ---------------------------------------------------------
+// The reference's loop (tetrahedra_tracer.cu:129-160) is serial in the samples only through its pointer p, which never moves
+// back: p_j = first p >= p_{j-1} with t_out[p] >= d_j.  When t_out is non-decreasing along the ray (checked per ray; true
+// unless sub-eps slivers were swapped by the pairing) this is a running maximum of independent lower bounds,
+// p_j = max_{i<=j} lower_bound(t_out, d_i) -- for sorted AND for unsorted samples -- so the warp takes 32 samples at a time:
+// binary search in shared memory, warp max-scan, carry.  Rays that fail the check run the literal loop on one lane.
+constexpr int MATCH_WARPS = 4;
+__global__ void __launch_bounds__(MATCH_WARPS * 32) k_match_warp(uint32_t R, uint32_t S, uint32_t M, const uint32_t *__restrict__ num,
+                                                                 const uint32_t *__restrict__ cells, const float2 *__restrict__ hd,
+                                                                 const float *__restrict__ bary, const float *__restrict__ sd,
+                                                                 const uint4 *__restrict__ verts, uint32_t *__restrict__ cell_out,
+                                                                 uint4 *__restrict__ verts_out, uint8_t *__restrict__ mask_out,
+                                                                 float *__restrict__ bary_out) {
+    extern __shared__ float s_tout[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * MATCH_WARPS + warp;
+    if (i >= R) return;
+    float *t_out = s_tout + (size_t)warp * M;
+    const uint32_t n = min(num[i], M);
+    const size_t row = (size_t)i * M;
+    for (uint32_t k = lane; k < n; k += 32) t_out[k] = hd[row + k].y;
+    __syncwarp();
+    bool mono = true;
+    for (uint32_t k = lane + 1; k < n; k += 32) mono = mono && !(t_out[k] < t_out[k - 1]);
+    mono = __all_sync(0xffffffffu, mono);
+    uint32_t carry = 0;     // the reference's pointer p after the previous sample
+    bool done = false;      // (only used by the literal fallback)
+    for (uint32_t base = 0; base < S; base += 32) {
+        const uint32_t j = base + (uint32_t)lane;
+        const bool valid = j < S;
+        const size_t g = (size_t)i * S + j;
+        const float cd = valid ? sd[g] : 0.f;
+        uint32_t p;
+        if (mono) {
+            uint32_t lo = 0, hi = valid ? n : 0u;  // first p with t_out[p] >= cd  (a NaN sample compares false: lo stays 0, as the loop)
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (t_out[mid] < cd) lo = mid + 1; else hi = mid; }
+            p = lo;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t q = __shfl_up_sync(0xffffffffu, p, o); if (lane >= o) p = max(p, q); }
+            p = max(p, carry);
+            carry = __shfl_sync(0xffffffffu, p, 31);
+        } else {
+            // literal pointer walk for this group of 32 samples, one lane, results broadcast
+            uint32_t mine = n;
+            if (lane == 0) {
+                for (uint32_t q = 0; q < 32 && base + q < S; ++q) {
+                    uint32_t pq = n;
+                    if (!done) {
+                        const float c = sd[(size_t)i * S + base + q];
+                        while (carry < n && t_out[carry] < c) carry++;
+                        if (carry >= n) done = true;
+                        pq = carry;
+                    }
+                    s_tout[MATCH_WARPS * (size_t)M + warp * 32 + q] = __uint_as_float(pq);
+                }
+            }
+            __syncwarp();
+            mine = __float_as_uint(s_tout[MATCH_WARPS * (size_t)M + warp * 32 + lane]);
+            __syncwarp();
+            p = mine;
+        }
+        if (!valid) continue;
+        uint32_t oc = TN_EMPTY;
+        uint4 ov = make_uint4(TN_EMPTY, TN_EMPTY, TN_EMPTY, TN_EMPTY);
+        uint8_t om = 0;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (p < n) {  // p >= n: "there will be no more matches on this ray" (:137-140)
+            const float2 h = hd[row + p];
+            if (h.x <= cd) {
+                om = 1;
+                oc = cells[row + p];
+                ov = verts[row + p];
+                const float mult = __fdiv_rn(__fsub_rn(cd, h.x), __fsub_rn(h.y, h.x));
+                const float omm = __fsub_rn(1.0f, mult);
+                const float *c = bary + 6 * (row + p);
+                b0 = __fadd_rn(__fmul_rn(omm, c[0]), __fmul_rn(mult, c[3]));
+                b1 = __fadd_rn(__fmul_rn(omm, c[1]), __fmul_rn(mult, c[4]));
+                b2 = __fadd_rn(__fmul_rn(omm, c[2]), __fmul_rn(mult, c[5]));
+            }
+        }
+        cell_out[g] = oc; verts_out[g] = ov; mask_out[g] = om;
+        bary_out[3 * g] = b0; bary_out[3 * g + 1] = b1; bary_out[3 * g + 2] = b2;
+    }
+}
+
 // ---- [C,V] -> [V,C] ---------------------------------------------------------------------------
 __global__ void k_transpose(const float *__restrict__ in, float *__restrict__ out, uint32_t rows, uint32_t cols) {
     __shared__ float tile[32][33];
@@ -197,9 +282,17 @@ extern "C" int tn_find_visited_cells(tn_tracer *h, uint32_t R, uint32_t S, uint3
     if (!h) return tn::fail(TN_ERR_ARG, "null tracer");
     if (R == 0 || S == 0) return TN_OK;
     tn::DeviceGuard g(h->device);
-    tn::k_match<<<(R + 63) / 64, 64, 0, (cudaStream_t)stream>>>(R, S, M, d_num, d_cells, (const float2 *)d_dist, d_bary, d_sample_dist,
-                                                               (const uint4 *)d_verts, d_cell_out, (uint4 *)d_verts_out, d_mask_out,
-                                                               d_bary_out);
+    const size_t smem = sizeof(float) * ((size_t)tn::MATCH_WARPS * M + tn::MATCH_WARPS * 32);
+    if (smem <= 200 * 1024) {
+        TN_CUDA(cudaFuncSetAttribute(tn::k_match_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tn::k_match_warp<<<(R + tn::MATCH_WARPS - 1) / tn::MATCH_WARPS, tn::MATCH_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            R, S, M, d_num, d_cells, (const float2 *)d_dist, d_bary, d_sample_dist, (const uint4 *)d_verts, d_cell_out, (uint4 *)d_verts_out,
+            d_mask_out, d_bary_out);
+    } else {  // absurdly large M: the literal one-thread-per-ray form
+        tn::k_match<<<(R + 63) / 64, 64, 0, (cudaStream_t)stream>>>(R, S, M, d_num, d_cells, (const float2 *)d_dist, d_bary, d_sample_dist,
+                                                                   (const uint4 *)d_verts, d_cell_out, (uint4 *)d_verts_out, d_mask_out,
+                                                                   d_bary_out);
+    }
     h->launches += 1;
     TN_CUDA(cudaGetLastError());
     return TN_OK;

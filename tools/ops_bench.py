@@ -49,5 +49,20 @@ for name, idx in (("random vertices", vi), ("runs of 2 samples per tetrahedron",
     r["forward_frac_of_hbm_peak"] = r["forward_GBs_algorithmic"] / peak
     res[name] = {k: round(v, 4) for k, v in r.items()}
     print(name, res[name], flush=True)
+# ---- find_visited_cells at configs[1] sizes: 4096 rays x 257 samples against a real trace of the 302k-tetrahedra mesh ----
+import bench
+from tetranerf import cpp
+from tetranerf.b200 import synthetic as syn
+Vm, Cm, _ = bench.make_workload()
+tr = cpp.TetrahedraTracer(dev); tr.load_tetrahedra(torch.from_numpy(Vm).to(dev), torch.from_numpy(Cm).to(dev))
+o, d = syn.camera_rays(4096, seed=3); o, d = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+out = tr.trace_rays(o, d, 512)
+hd = out["hit_distances"]; nv = out["num_visited_cells"].long().clamp_min(1)
+near = hd[:, 0, 0:1]; far = torch.gather(hd[..., 1], 1, (nv - 1)[:, None])
+dist = near + (far - near) * (torch.arange(257, device=dev)[None] + 0.5) / 257
+fv = lambda: tr.find_visited_cells(out["num_visited_cells"], out["visited_cells"], out["barycentric_coordinates"], out["hit_distances"], out["vertex_indices"], dist)
+res["find_visited_cells_ms (4096 x 257)"] = round(timeit(fv), 4)
+res["trace_rays_dense_ms (4096, M=512)"] = round(timeit(lambda: tr.trace_rays(o, d, 512)), 4)
+print({k: v for k, v in res.items() if "ms (" in k}, flush=True)
 os.makedirs(R_ + "/gpurun_out", exist_ok=True)
 json.dump(res, open(R_ + "/gpurun_out/r1_ops_bench.json", "w"), indent=1)
