@@ -177,6 +177,38 @@ __global__ void k_interp_rows(uint32_t N, uint32_t C, const uint32_t *__restrict
         out[(size_t)i * C + j] = o;
     }
 }
+// C == 64 (the model's field_dim): half a warp per sample, 4 features per lane -> every vertex row is one 256-byte burst of
+// 16-byte loads and two samples share each instruction; same FMA chain per element as k_interp_rows
+template <int D>
+__global__ void k_interp_rows64(uint32_t N, const uint32_t *__restrict__ vi, const float *__restrict__ w, const float4 *__restrict__ frow,
+                                float4 *__restrict__ out) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const uint32_t l16 = threadIdx.x & 15u;
+    if (i >= N) return;
+    uint32_t v[D];
+    float wk[D];
+    float weight = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = vi[(size_t)i * D + k];
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) { wk[k] = w[(size_t)i * (D - 1) + k]; weight = __fadd_rn(weight, wk[k]); }
+    const float w0 = __fsub_rn(1.0f, weight);
+    float4 f[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) f[k] = v[k] != TN_EMPTY ? __ldg(frow + (size_t)v[k] * 16 + l16) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k)
+        if (v[k + 1] != TN_EMPTY) {
+            o.x = __fmaf_rn(wk[k], f[k + 1].x, o.x); o.y = __fmaf_rn(wk[k], f[k + 1].y, o.y);
+            o.z = __fmaf_rn(wk[k], f[k + 1].z, o.z); o.w = __fmaf_rn(wk[k], f[k + 1].w, o.w);
+        }
+    if (v[0] != TN_EMPTY) {
+        o.x = __fmaf_rn(w0, f[0].x, o.x); o.y = __fmaf_rn(w0, f[0].y, o.y);
+        o.z = __fmaf_rn(w0, f[0].z, o.z); o.w = __fmaf_rn(w0, f[0].w, o.w);
+    }
+    out[(size_t)i * 16 + l16] = o;
+}
 // feature-major field [C,V] read in place (no scratch): thread per (sample, feature)
 template <int D>
 __global__ void k_interp_cols(uint32_t N, uint32_t C, uint32_t V, const uint32_t *__restrict__ vi, const float *__restrict__ w,
@@ -224,7 +256,10 @@ static int interp_fwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t *vi, co
         dim3 tb(32, 8), tg((V + 31) / 32, (C + 31) / 32);
         k_transpose<<<tg, tb, 0, s>>>(field, scratch, C, V);
         const uint32_t threads = 256;
-        k_interp_rows<D><<<(uint32_t)(((size_t)N * 32 + threads - 1) / threads), threads, 0, s>>>(N, C, vi, w, scratch, out);
+        if (C == 64 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)scratch & 15) == 0)
+            k_interp_rows64<D><<<(uint32_t)(((size_t)N * 16 + threads - 1) / threads), threads, 0, s>>>(N, vi, w, (const float4 *)scratch, (float4 *)out);
+        else
+            k_interp_rows<D><<<(uint32_t)(((size_t)N * 32 + threads - 1) / threads), threads, 0, s>>>(N, C, vi, w, scratch, out);
     } else {
         const size_t total = (size_t)N * C;
         k_interp_cols<D><<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(N, C, V, vi, w, field, out);
