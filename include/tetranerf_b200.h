@@ -79,6 +79,11 @@ int tn_find_visited_cells(tn_tracer *h, uint32_t R, uint32_t S, uint32_t M, cons
  *   moveaxis view).  D in {2,3,4,6}.  d_scratch: NULL, or >= C*V floats used for a [V,C] shadow. */
 int tn_interpolate_values(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi, const float *d_w,
                           const float *d_field, float *d_out, float *d_scratch, void *stream);
+/* the [V,C] shadow on its own, and interpolate_values reading a shadow built earlier (d_field of tn_interpolate_values
+ * may be NULL when d_scratch already holds the shadow): a training step interpolates the same field twice */
+int tn_make_field_shadow(int device, uint32_t C, uint32_t V, const float *d_field, float *d_shadow, void *stream);
+int tn_interpolate_values_shadow(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi, const float *d_w,
+                                 const float *d_shadow, float *d_out, void *stream);
 /* interpolate_values_backward<D> -- src/py_binding.cpp:341-372, src/tetrahedra_tracer.cu:223-248.
  *   d_grad_in f32[N,C], d_grad_field f32[C,V] (every element written by this call, py_binding.cpp:360).
  *   d_scratch: NULL (scalar atomics straight into the feature-major gradient, as the reference), or >= C*V floats for
@@ -126,6 +131,11 @@ int tn_debug_trace_stats(tn_tracer *h, uint32_t *out2);
 int tn_render_debug_buffers(tn_tracer *h, void **ptrs16);
 /* one 128x128 tile out = A[128,K] * W[128,K]^T through the tcgen05 bf16x3 path; K in {64,128}; synchronous */
 int tn_debug_gemm_bf16x3(int device, const float *d_A, const float *d_W, uint32_t K, float *d_out, void *stream);
+/* probe of the shared-memory operand forms of the fused MLP backward: P, Q f32[128,128] staged as bf16 hi/lo blocks
+ * ([rows][64 columns], 128-byte swizzle); mode 0: out = P Q^T (both K-major), 1: out = P Q (B MN-major), 2: out = P^T Q (both
+ * MN-major); N in {64,128}; lbo / sbo / kstep (bytes) describe the MN-major descriptors; synchronous */
+int tn_debug_gemm_modes(int device, int mode, uint32_t N, uint32_t lbo, uint32_t sbo, uint32_t kstep, const float *d_P,
+                        const float *d_Q, float *d_out, void *stream);
 /* microbenchmark behind tools/mma_rate.py: cycles for nrep x 8 tcgen05.mma (M128 N128 K16 bf16); mode bit 0: two accumulators,
  * bit 1: A from shared memory instead of TMEM, bit 2: concurrent tcgen05.ld/st traffic; h_out2 = {issue cycles, issue+drain} */
 int tn_debug_mma_rate(int device, int nrep, int mode, uint32_t boff, long long *h_out2);

@@ -83,10 +83,22 @@ def test_fused_render_vs_oracle(small_mesh, cfgname, field_kind):
     print("fine bins max abs err", (eb_f - aux["fine_euclid"][order]).abs().max().item())
     torch.testing.assert_close(eb_f, aux["fine_euclid"][order], rtol=1e-4, atol=1e-4)
     outf = _from_ptr(bufs["out_f"], (n_act, S2, 4), torch.float32).cpu()
-    # per-sample values are compared where the fine bins agree closely (a sample may legitimately flip tetrahedron at 1e-7)
+    # north_star: fp32 colour/density within 1e-4 abs PER SAMPLE.  The fine sample positions agree to ~1e-7 only (PDF
+    # inversion in fp32), so a sample sitting on a face may legitimately land in the neighbouring tetrahedron ("flip"):
+    # those are excluded -- and counted -- everything else is asserted.
+    vi_gpu = _from_ptr(bufs["vi_f"], (n_act, S2, 4), torch.int32).cpu()
+    vi_ref = torch.from_numpy(aux["matched"]["vertex_indices"])[order]
+    flipped = (vi_gpu != vi_ref).any(-1)
     sig_err = (outf[..., 0] - aux["sigmas"][order][..., 0]).abs()
-    col_err = (outf[..., 1:] - aux["colors"][order]).abs()
-    print("sigma err: max", sig_err.max().item(), "median", sig_err.median().item(), " colour err max", col_err.max().item())
+    col_err = (outf[..., 1:] - aux["colors"][order]).abs().amax(-1)
+    flip_rate = flipped.float().mean().item()
+    print(f"sigma err: max {sig_err[~flipped].max().item():.2e} median {sig_err.median().item():.2e}  colour err max "
+          f"{col_err[~flipped].max().item():.2e}  flipped samples {int(flipped.sum())} ({100 * flip_rate:.3f} %)")
+    assert flip_rate < 2e-3, flip_rate
+    # density: 1e-4 absolute, or relative where sigma is large (softplus is the identity there and fp32 itself has ~1e-6 relative)
+    sig_ref = aux["sigmas"][order][..., 0]
+    assert bool((sig_err[~flipped] <= 1e-4 + 2e-5 * sig_ref[~flipped].abs()).all()), sig_err[~flipped].max().item()
+    assert col_err[~flipped].max().item() <= 1e-4, col_err[~flipped].max().item()
     # ---- pixels ----
     e_rgb = (out["rgb"].cpu() - ref["rgb"]).abs().max().item()
     e_acc = (out["accumulation"].cpu() - ref["accumulation"]).abs().max().item()
@@ -95,6 +107,29 @@ def test_fused_render_vs_oracle(small_mesh, cfgname, field_kind):
     assert e_rgb < 1e-4 and e_acc < 1e-4
     # median depth is a step function of the cumulative weights: allow a handful of rays to pick the neighbouring sample
     assert (e_dep.flatten() > 1e-4).sum().item() <= max(2, len(o) // 100)
+
+
+@pytest.mark.parametrize("biased", [False, True])
+def test_fused_render_single_pass(small_mesh, biased):
+    """num_fine_samples == 0 (model.py:573: the PDF pass is skipped, colours come from the first pass)"""
+    from tetranerf.b200.render import RenderSettings
+
+    V, C = small_mesh
+    tr, fr, field, params = setup(V, C)
+    o, d = syn.camera_rays(200, seed=9)
+    o[7] = [5, 5, 5]; d[7] = [1, 0, 0]
+    st = RenderSettings(num_samples=96, num_fine_samples=0, use_biased_sampler=biased)
+    oc = orc.RenderConfig(num_samples=96, num_fine_samples=0, use_biased_sampler=biased)
+    out = fr.render(torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), st)
+    tr.synchronize()
+    ref = orc.render(orc.OracleMesh(V, C), torch.from_numpy(field), params, o, d, oc)
+    assert torch.equal(out["ray_mask"].cpu(), ref["ray_mask"])
+    e_rgb = (out["rgb"].cpu() - ref["rgb"]).abs().max().item()
+    e_acc = (out["accumulation"].cpu() - ref["accumulation"]).abs().max().item()
+    e_dep = (out["depth"].cpu() - ref["depth"]).abs()
+    print(f"single pass biased={biased}: max|rgb| {e_rgb:.2e} max|acc| {e_acc:.2e} depth max {e_dep.max().item():.2e}")
+    assert e_rgb < 1e-4 and e_acc < 1e-4
+    assert (e_dep.flatten() > 1e-4).sum().item() <= 2
 
 
 def test_fused_render_is_deterministic_and_reusable(small_mesh):

@@ -169,3 +169,94 @@ extern "C" int tn_debug_mma_rate(int device, int nrep, int mode, uint32_t boff, 
     cudaFree(d);
     return TN_OK;
 }
+
+// ---- probe for the operand forms of the fused MLP backward (tn_mlp_bwd.cuh): every operand is a [128 rows][128 cols] fp32
+// matrix staged in shared memory as bf16 hi/lo in the ONE layout the backward kernel uses -- per 64-column block:
+// [hi 16 KB][lo 16 KB], rows of 128 bytes, 128-byte swizzle -- and is read either K-major (the K index runs along the
+// columns) or MN-major (the K index runs along the ROWS; the M/N index along the columns: bit 15 / 16 of the instruction
+// descriptor).  mode 0: out = P Q^T (A, B K-major: the forward form);  mode 1: out = P Q (A K-major, B MN-major: dX = dA W);
+// mode 2: out = P^T Q (A, B MN-major: dW = dA^T H).  N in {64, 128} (mode 0: rows of Q; modes 1, 2: columns of Q).
+namespace tn {
+using namespace tc;
+__device__ __forceinline__ uint64_t make_desc_rt(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__global__ void __launch_bounds__(160, 1) k_debug_gemm2(const float *__restrict__ P, const float *__restrict__ Q, int mode, uint32_t N,
+                                                         uint32_t lbo, uint32_t sbo, uint32_t kstep, float *__restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *p_s = smem, *q_s = smem + 65536;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 131072);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + 131072 + 64);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 4) {
+        if (lane == 0) { mbar_init(&bars[0], 1); fence_barrier_init(); }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 128);
+    } else {
+        const uint32_t row = threadIdx.x;
+        for (uint32_t k = 0; k < 128; k += 2) {
+            uint32_t hi, lo;
+            const uint32_t off = (k >> 6) * 32768u + sw128_offset(row, k & 63u);
+            split_pack2(P[row * 128 + k], P[row * 128 + k + 1], hi, lo);
+            *reinterpret_cast<uint32_t *>(p_s + off) = hi;
+            *reinterpret_cast<uint32_t *>(p_s + off + 16384u) = lo;
+            split_pack2(Q[row * 128 + k], Q[row * 128 + k + 1], hi, lo);
+            *reinterpret_cast<uint32_t *>(q_s + off) = hi;
+            *reinterpret_cast<uint32_t *>(q_s + off + 16384u) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *tmem_ptr;
+    if (warp == 4 && lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N) | (mode == 2 ? (1u << 15) : 0u) | (mode >= 1 ? (1u << 16) : 0u);
+        const uint32_t pa = smem_u32(p_s), qa = smem_u32(q_s);
+        uint32_t acc = 0;
+        for (int term = 0; term < 3; ++term) {  // (P_hi,Q_hi) (P_lo,Q_hi) (P_hi,Q_lo)
+            const uint32_t po = term == 1 ? 16384u : 0u, qo = term == 2 ? 16384u : 0u;
+            for (uint32_t j = 0; j < 8; ++j) {  // 8 k-steps of 16
+                // K-major: k-step j lives in column block j/4 at byte 32 (j%4) of every row; MN-major: rows 16j.. of every block
+                const uint64_t da = mode == 2 ? make_desc_rt(pa + po + j * kstep, lbo, sbo) : make_desc_sw128(pa + po + (j >> 2) * 32768u + (j & 3u) * 32u);
+                const uint64_t db = mode >= 1 ? make_desc_rt(qa + qo + j * kstep, lbo, sbo) : make_desc_sw128(qa + qo + (j >> 2) * 32768u + (j & 3u) * 32u);
+                mma_ss(tbase, da, db, idesc, acc);
+                acc = 1;
+            }
+        }
+        mma_commit(&bars[0]);
+    }
+    if (warp < 4) {
+        mbar_wait(&bars[0], 0);
+        fence_after_sync();
+        const uint32_t row = threadIdx.x;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (uint32_t ch = 0; ch < N / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(tbase + lane_base + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) out[row * 128 + ch * 32 + i] = __uint_as_float(r[i]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tbase, 128);
+}
+}  // namespace tn
+
+// test hook: d_P, d_Q f32[128,128], d_out f32[128,128] (first N columns written); lbo / sbo / kstep in bytes describe the
+// MN-major operands (the backward kernel uses lbo = 32768 (next 64-column block), sbo = 1024 (next 8 rows), kstep = 2048)
+extern "C" int tn_debug_gemm_modes(int device, int mode, uint32_t N, uint32_t lbo, uint32_t sbo, uint32_t kstep, const float *d_P,
+                                   const float *d_Q, float *d_out, void *stream) {
+    if (mode < 0 || mode > 2 || (N != 64 && N != 128)) return tn::fail(TN_ERR_ARG, "tn_debug_gemm_modes: mode in 0..2, N in {64,128}");
+    tn::DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int smem = 131072 + 128;
+    TN_CUDA(cudaFuncSetAttribute(tn::k_debug_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tn::k_debug_gemm2<<<1, 160, smem, s>>>(d_P, d_Q, mode, N, lbo, sbo, kstep, d_out);
+    TN_CUDA(cudaGetLastError());
+    TN_CUDA(cudaStreamSynchronize(s));
+    return TN_OK;
+}

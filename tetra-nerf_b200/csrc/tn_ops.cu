@@ -138,9 +138,11 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_match_warp(uint32_t R, uin
 }
 
 // ---- [C,V] -> [V,C] ---------------------------------------------------------------------------
-__global__ void k_transpose(const float *__restrict__ in, float *__restrict__ out, uint32_t rows, uint32_t cols) {
+// rows_on_x: the row tiles are indexed by blockIdx.x (the grid's y extent is limited to 65535 blocks: the LONG dimension,
+// the vertex count, must always travel on x)
+__global__ void k_transpose(const float *__restrict__ in, float *__restrict__ out, uint32_t rows, uint32_t cols, bool rows_on_x) {
     __shared__ float tile[32][33];
-    const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const uint32_t bx = (rows_on_x ? blockIdx.y : blockIdx.x) * 32, by = (rows_on_x ? blockIdx.x : blockIdx.y) * 32;
     for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
         const uint32_t y = by + r, x = bx + threadIdx.x;
         if (y < rows && x < cols) tile[r][threadIdx.x] = in[(size_t)y * cols + x];
@@ -249,12 +251,15 @@ __global__ void k_interp_bwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t 
     if (v0 != TN_EMPTY) atomicAdd(&gfield[(size_t)j * V + v0], __fmul_rn(__fsub_rn(1.0f, weight), g));
 }
 
+// field == nullptr: `scratch` already holds the [V,C] shadow of the field (tn_make_field_shadow)
 template <int D>
 static int interp_fwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t *vi, const float *w, const float *field, float *out,
                       float *scratch, cudaStream_t s) {
     if (scratch) {
-        dim3 tb(32, 8), tg((V + 31) / 32, (C + 31) / 32);
-        k_transpose<<<tg, tb, 0, s>>>(field, scratch, C, V);
+        if (field != nullptr) {
+            dim3 tb(32, 8), tg((V + 31) / 32, (C + 31) / 32);
+            k_transpose<<<tg, tb, 0, s>>>(field, scratch, C, V, false);
+        }
         const uint32_t threads = 256;
         if (C == 64 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)scratch & 15) == 0)
             k_interp_rows64<D><<<(uint32_t)(((size_t)N * 16 + threads - 1) / threads), threads, 0, s>>>(N, vi, w, (const float4 *)scratch, (float4 *)out);
@@ -296,14 +301,14 @@ template <int D>
 static int interp_bwd(uint32_t N, uint32_t C, uint32_t V, const uint32_t *vi, const float *w, const float *gin, float *gfield,
                       float *scratch, cudaStream_t s) {
     if (scratch && (C & 3u) == 0 && ((uintptr_t)gin & 15) == 0 && ((uintptr_t)scratch & 15) == 0) {
-        cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)C * V, s);
+        TN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)C * V, s));
         const size_t total = (size_t)N * (C / 4);
         k_interp_bwd_rows<D><<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(N, C / 4, vi, w, (const float4 *)gin, (float4 *)scratch);
-        dim3 tb(32, 8), tg((C + 31) / 32, (V + 31) / 32);
-        k_transpose<<<tg, tb, 0, s>>>(scratch, gfield, V, C);  // [V,C] -> [C,V]
+        dim3 tb(32, 8), tg((V + 31) / 32, (C + 31) / 32);
+        k_transpose<<<tg, tb, 0, s>>>(scratch, gfield, V, C, true);  // [V,C] -> [C,V]
         return TN_OK;
     }
-    cudaMemsetAsync(gfield, 0, sizeof(float) * (size_t)C * V, s);  // py_binding.cpp:360
+    TN_CUDA(cudaMemsetAsync(gfield, 0, sizeof(float) * (size_t)C * V, s));  // py_binding.cpp:360
     const size_t total = (size_t)N * C;
     k_interp_bwd<D><<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(N, C, V, vi, w, gin, gfield);
     return TN_OK;
@@ -338,15 +343,33 @@ extern "C" int tn_interpolate_values(int device, uint32_t D, uint32_t N, uint32_
     if (N == 0 || C == 0) return TN_OK;
     tn::DeviceGuard g(device);
     cudaStream_t s = (cudaStream_t)stream;
+    int rc = TN_OK;
     switch (D) {  // py_binding.cpp:258-276
-        case 2: tn::interp_fwd<2>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
-        case 3: tn::interp_fwd<3>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
-        case 4: tn::interp_fwd<4>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
-        case 6: tn::interp_fwd<6>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
+        case 2: rc = tn::interp_fwd<2>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
+        case 3: rc = tn::interp_fwd<3>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
+        case 4: rc = tn::interp_fwd<4>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
+        case 6: rc = tn::interp_fwd<6>(N, C, V, d_vi, d_w, d_field, d_out, d_scratch, s); break;
         default: return tn::fail(TN_ERR_ARG, "Unsupported interpolation dimension with value " + std::to_string(D));
     }
+    if (rc) return rc;
     TN_CUDA(cudaGetLastError());
     return TN_OK;
+}
+
+// [C,V] feature-major field -> [V,C] row-major shadow (one vertex = one contiguous row); callers that interpolate the same
+// field more than once (coarse + fine pass of a training step) build it once and use tn_interpolate_values_shadow
+extern "C" int tn_make_field_shadow(int device, uint32_t C, uint32_t V, const float *d_field, float *d_shadow, void *stream) {
+    if (C == 0 || V == 0) return TN_OK;
+    tn::DeviceGuard g(device);
+    dim3 tb(32, 8), tg((V + 31) / 32, (C + 31) / 32);
+    tn::k_transpose<<<tg, tb, 0, (cudaStream_t)stream>>>(d_field, d_shadow, C, V, false);
+    TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+extern "C" int tn_interpolate_values_shadow(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi, const float *d_w,
+                                            const float *d_shadow, float *d_out, void *stream) {
+    if (!d_shadow) return tn::fail(TN_ERR_ARG, "tn_interpolate_values_shadow: null shadow");
+    return tn_interpolate_values(device, D, N, C, V, d_vi, d_w, nullptr, d_out, const_cast<float *>(d_shadow), stream);
 }
 
 extern "C" int tn_interpolate_values_backward(int device, uint32_t D, uint32_t N, uint32_t C, uint32_t V, const uint32_t *d_vi,
@@ -357,13 +380,15 @@ extern "C" int tn_interpolate_values_backward(int device, uint32_t D, uint32_t N
         TN_CUDA(cudaMemsetAsync(d_grad_field, 0, sizeof(float) * (size_t)C * V, s));  // py_binding.cpp:360
         return TN_OK;
     }
+    int rc = TN_OK;
     switch (D) {  // py_binding.cpp:278-296
-        case 2: tn::interp_bwd<2>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
-        case 3: tn::interp_bwd<3>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
-        case 4: tn::interp_bwd<4>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
-        case 6: tn::interp_bwd<6>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
+        case 2: rc = tn::interp_bwd<2>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
+        case 3: rc = tn::interp_bwd<3>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
+        case 4: rc = tn::interp_bwd<4>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
+        case 6: rc = tn::interp_bwd<6>(N, C, V, d_vi, d_w, d_grad_in, d_grad_field, d_scratch, s); break;
         default: return tn::fail(TN_ERR_ARG, "Unsupported interpolation dimension with value " + std::to_string(D));
     }
+    if (rc) return rc;
     TN_CUDA(cudaGetLastError());
     return TN_OK;
 }

@@ -285,6 +285,35 @@ __device__ void weights_from_density(float *dd, float *tr, uint32_t S, int lane)
     __syncwarp();
 }
 
+// direction encoding folded into a per-ray bias of mlp_head (model.py:607-620): dirbias[slot] = b4 + W4[:, :27] . enc(dir)
+// NeRFEncoding(in_dim=3, num_frequencies=4, min_freq_exp=0, max_freq_exp=4, include_input=True), model.py:426-432
+__device__ __forceinline__ void dir_bias(const SampleParams &p, uint32_t ray, uint32_t slot, int lane) {
+    const float dx = p.d[3 * (size_t)ray], dy = p.d[3 * (size_t)ray + 1], dz = p.d[3 * (size_t)ray + 2];
+    float enc[27];
+    {
+        const float dd[3] = {dx, dy, dz};
+        const float two_pi = 6.283185307179586f, half_pi = 1.5707963267948966f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float sc = two_pi * dd[a];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const float freq = f == 0 ? 1.0f : (f == 1 ? 2.5198421f : (f == 2 ? 6.3496042f : 16.0f));  // 2**linspace(0,4,4)
+                const float si = sc * freq;
+                enc[a * 4 + f] = sinf(si);
+                enc[12 + a * 4 + f] = sinf(si + half_pi);
+            }
+            enc[24 + a] = dd[a];
+        }
+    }
+    for (uint32_t o = lane; o < 128; o += 32) {
+        float acc = p.w4dir[128 * 27 + o];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) acc = fmaf(__ldg(p.w4dir + o * 27 + k), enc[k], acc);
+        p.dirbias[(size_t)slot * 128 + o] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_fine(const SampleParams p) {
     extern __shared__ float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -363,32 +392,7 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_fine(const SampleP
         p.vi_f[g] = vi;
         p.bary_f[3 * g] = b0; p.bary_f[3 * g + 1] = b1; p.bary_f[3 * g + 2] = b2;
     }
-    // ---- direction encoding folded into a per-ray bias of mlp_head (model.py:607-620) ----
-    // NeRFEncoding(in_dim=3, num_frequencies=4, min_freq_exp=0, max_freq_exp=4, include_input=True), model.py:426-432
-    const float dx = p.d[3 * (size_t)ray], dy = p.d[3 * (size_t)ray + 1], dz = p.d[3 * (size_t)ray + 2];
-    float enc[27];
-    {
-        const float dd[3] = {dx, dy, dz};
-        const float two_pi = 6.283185307179586f, half_pi = 1.5707963267948966f;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float sc = two_pi * dd[a];
-#pragma unroll
-            for (int f = 0; f < 4; ++f) {
-                const float freq = f == 0 ? 1.0f : (f == 1 ? 2.5198421f : (f == 2 ? 6.3496042f : 16.0f));  // 2**linspace(0,4,4)
-                const float si = sc * freq;
-                enc[a * 4 + f] = sinf(si);
-                enc[12 + a * 4 + f] = sinf(si + half_pi);
-            }
-            enc[24 + a] = dd[a];
-        }
-    }
-    for (uint32_t o = lane; o < 128; o += 32) {
-        float acc = p.w4dir[128 * 27 + o];
-#pragma unroll
-        for (int k = 0; k < 27; ++k) acc = fmaf(__ldg(p.w4dir + o * 27 + k), enc[k], acc);
-        p.dirbias[(size_t)slot * 128 + o] = acc;
-    }
+    dir_bias(p, ray, slot, lane);
 }
 
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_composite(const SampleParams p) {
@@ -430,9 +434,14 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_composite(const SamplePar
     }
 }
 
-// single-pass configuration (num_fine_samples == 0): colours come from the first and only pass; handled by
-// running the FINE MLP on the coarse samples (dirbias computed by k_dirbias_only).
-__global__ void k_dirbias_only(const SampleParams p) { /* reserved */ }
+// single-pass configuration (num_fine_samples == 0, model.py:573 skipped): colours come from the first and only pass -- the
+// FINE MLP runs on the coarse samples and only the per-ray direction bias is still missing
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_dirbias_only(const SampleParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * SAMPLE_WARPS + warp;
+    if (slot >= *p.n_active) return;
+    dir_bias(p, p.ray_list[slot], slot, lane);
+}
 
 static int ensure_ws(RenderState *r, size_t R, size_t M, size_t Sc, size_t S2) {
     if (R <= r->cap_R && M <= r->cap_M && Sc <= r->cap_Sc && S2 <= r->cap_S2) return TN_OK;
@@ -495,9 +504,9 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     if (r->V != h->mesh.V) return fail(TN_ERR_ARG, "tn_render: field has a different vertex count than the mesh");
     const uint32_t M = cfg->max_ray_triangles, Sc = cfg->num_samples, Sf = cfg->num_fine_samples;
     if (Sc == 0 || Sc > 4096 || Sf > 4096) return fail(TN_ERR_ARG, "tn_render: num_samples must be in [1,4096]");
-    if (Sf == 0) return fail(TN_ERR_ARG, "tn_render: num_fine_samples == 0 is not supported by the fused path (use the unfused ops)");
     if (R == 0) return TN_OK;
-    const uint32_t S2 = Sc + Sf + 1;  // PDFSampler include_original (model.py:463)
+    const bool single = Sf == 0;                       // one pass only: the colours come from the coarse samples
+    const uint32_t S2 = single ? Sc : Sc + Sf + 1;     // PDFSampler include_original (model.py:463)
     DeviceGuard g(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = ensure_ws(r, R, M, Sc, S2);
@@ -542,12 +551,15 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     mc.bias = r->bias; mc.head = r->head; mc.dirbias = nullptr; mc.out = r->dens_c;
     mc.tile_ctr = r->n_active + 1;  // words 1, 2 of the zeroed 16-byte block: tile counters of the coarse / fine pass
     const uint32_t tiles_c = (uint32_t)(((uint64_t)R * Sc + 127) / 128), tiles_f = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
-    k_mlp<false><<<std::min<uint32_t>(tiles_c, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mc);
+    if (!single) k_mlp<false><<<std::min<uint32_t>(tiles_c, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mc);
     TN_EV(3);
-    k_sample_fine<<<gridR, SAMPLE_WARPS * 32, smem_sf, s>>>(p);
+    if (!single) k_sample_fine<<<gridR, SAMPLE_WARPS * 32, smem_sf, s>>>(p);
+    else k_dirbias_only<<<gridR, SAMPLE_WARPS * 32, 0, s>>>(p);
     TN_EV(4);
     MlpParams mf = mc;
-    mf.S = S2; mf.vi = r->vi_f; mf.bary = r->bary_f; mf.dirbias = r->dirbias; mf.out = r->out_f;
+    mf.S = S2; mf.dirbias = r->dirbias; mf.out = r->out_f;
+    if (!single) { mf.vi = r->vi_f; mf.bary = r->bary_f; }
+    else p.ebins_f = r->ebins_c;  // k_composite integrates over the coarse bins
     mf.timeline = g_timeline;
     mf.tile_ctr = r->n_active + 2;
     k_mlp<true><<<std::min<uint32_t>(tiles_f, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mf);

@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 7) k_trace(const TraceParams
                 __syncwarp();
             }
         }
-        if (p.ovf_list != nullptr && nh > ((p.scap + p.lcap) >> 1)) deferred = true;  // tts staging: 8 bytes per hit
+        // pairing stage: tts[] (8 bytes per hit) is staged over the work list ONLY (scap * 4 bytes); emit[] lives in leafq
+        if (p.ovf_list != nullptr && nh > (p.scap >> 1)) deferred = true;
         if (deferred) {  // uniform per warp
             if (lane == 0) p.ovf_list[atomicAdd(p.ovf_count, 1u)] = ray;
             __syncwarp();
@@ -509,19 +510,15 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
         int rc = launch_walk(h, o, d, R, M, num, cells, bary, dist, verts, h->d_walk_keys, h->d_ovf_list, list_count, solo_walk && !thread_walk, s);
         if (rc) return rc;
         p.dense = 0;
-        p.hcap = M + 128; p.scap = M > 512 ? 2 * M : 1024; p.lcap = M > 512 ? M / 2 : 320;
+        p.hcap = M + 128; p.scap = 4096; p.lcap = M > 512 ? M / 2 : 320;
         p.ray_count = list_count; p.ray_list = h->d_ovf_list; p.keys_in = h->d_walk_keys;
         rc = launch((uint32_t)sms);
         if (rc) return rc;
         if (dense) return launch_tail_fill(h, R, M, num, cells, bary, dist, verts, s);
         return TN_OK;
     }
-    if (M <= 256) {
-        // one launch: the hit buffer (M + 128 keys) is small enough for 28 rays in flight per SM
-        p.hcap = M + 128; p.scap = 640; p.lcap = 320;
-        return launch(want);
-    }
-    // phase 1: M keys per ray (7.75 KB of shared memory per ray -> 28 rays per SM); rays that fill it are deferred
+    // phase 1: min(M + 128, 512) keys per ray (7.75 KB of shared memory per ray at M = 512 -> 28 rays per SM); rays whose hits
+    // or work list do not fit are deferred to phase 2 (never dropped)
     if (h->ovf_cap < R) {
         cudaFree(h->d_ovf_list);
         h->d_ovf_list = nullptr; h->ovf_cap = 0;
@@ -530,11 +527,12 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
     }
     uint32_t *ovf_count = reinterpret_cast<uint32_t *>(h->d_flags + 2);
     TN_CUDA(cudaMemsetAsync(ovf_count, 0, sizeof(uint32_t), s));
-    p.hcap = M; p.scap = 640; p.lcap = 320; p.ovf_count = ovf_count; p.ovf_list = h->d_ovf_list;
+    p.hcap = M <= 256 ? M + 128 : M; p.scap = 640; p.lcap = 320; p.ovf_count = ovf_count; p.ovf_list = h->d_ovf_list;
     int rc = launch(want);
     if (rc) return rc;
-    // phase 2: the deferred rays with the full streaming buffer (M + 128 keys); exits at once when there are none
-    p.hcap = M + 128; p.scap = M > 512 ? 2 * M : 1024; p.lcap = M > 512 ? M / 2 : 320;
+    // phase 2: the deferred rays with the full streaming buffer (M + 128 keys) and a 4096-entry work list; exits at once
+    // when there are none.  A work list overflow HERE is counted in d_flags[0] and reported by tn_synchronize.
+    p.hcap = M + 128; p.scap = 4096; p.lcap = M > 512 ? M / 2 : 320;
     p.ovf_count = nullptr; p.ovf_list = nullptr; p.ray_count = ovf_count; p.ray_list = h->d_ovf_list;
     return launch((uint32_t)sms);
 }

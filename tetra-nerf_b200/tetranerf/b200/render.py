@@ -118,26 +118,3 @@ class FusedRenderer:
         names = ["num", "dist", "n_active", "ray_list", "ebins_c", "sbins_c", "vi_c", "bary_c", "dens_c", "ebins_f", "vi_f", "bary_f",
                  "out_f", "dirbias", "fshadow", "wimg"]
         return {n: arr[i] for i, n in enumerate(names)}
-
-
-def smoke_check(tracer, V, Cells, o, d):
-    """used by __graft_entry__.smoke(): one small fused render vs the CPU oracle (1e-4 abs)."""
-    import numpy as np
-
-    from oracle import oracle as orc
-    from . import synthetic as syn
-
-    dev = tracer.device
-    field = syn.random_field(len(V), 64, seed=3)
-    params = orc.init_mlp_params(0)
-    fr = FusedRenderer(tracer)
-    fr.set_field(torch.from_numpy(field).to(dev))
-    fr.set_weights(params)
-    st = RenderSettings.tetra_nerf()
-    out = fr.render(torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev), st)
-    tracer.synchronize()
-    ref = orc.render(orc.OracleMesh(V, Cells), torch.from_numpy(field), params, o, d, orc.RenderConfig.tetra_nerf())
-    err = (out["rgb"].cpu() - ref["rgb"]).abs().max().item()
-    assert err < 1e-4, f"smoke: fused render rgb differs from the oracle by {err}"
-    assert torch.equal(out["ray_mask"].cpu(), ref["ray_mask"])
-    print(f"smoke ok: fused render max |rgb - oracle| = {err:.2e}")

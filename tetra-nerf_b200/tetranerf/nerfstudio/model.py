@@ -264,7 +264,7 @@ class TetrahedraNerf(Model):
     # ---- fused inference path ---------------------------------------------------------------------------
     def _fused_supported(self) -> bool:
         c = self.config
-        return (c.field_dim == 64 and c.hidden_size == 128 and c.num_density_layers == 3 and c.num_color_layers == 1 and c.num_fine_samples > 0
+        return (c.field_dim == 64 and c.hidden_size == 128 and c.num_density_layers == 3 and c.num_color_layers == 1
                 and c.input_fourier_frequencies == 0 and c.appearance_embed_dim == 0 and c.background_color in ("white", "black"))
 
     def _fused_renderer(self):

@@ -34,6 +34,8 @@ _lib.tn_find_tetrahedra.argtypes = [_vp, _vp, _u32, _vp, _vp, _vp, _vp]
 _lib.tn_find_visited_cells.argtypes = [_vp, _u32, _u32, _u32] + [_vp] * 11
 _lib.tn_interpolate_values.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]
 _lib.tn_interpolate_values_backward.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]
+_lib.tn_make_field_shadow.argtypes = [_i, _u32, _u32, _vp, _vp, _vp]
+_lib.tn_interpolate_values_shadow.argtypes = [_i, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]
 _lib.tn_debug_trace_stats.argtypes = [_vp, C.POINTER(_u32)]
 _lib.tn_set_walk_min_rays.argtypes = [_vp, _u32]
 _lib.tn_set_walk_solo_range.argtypes = [_vp, _u32, _u32]
@@ -269,10 +271,28 @@ def interpolate_values(vertex_indices: torch.Tensor, barycentric_coordinates: to
     Cdim, V = field.size(0), field.size(-1)
     dev = field.device
     out = torch.empty(list(vertex_indices.shape[:-1]) + [Cdim], dtype=torch.float32, device=dev)
-    scratch = torch.empty((V, Cdim), dtype=torch.float32, device=dev)  # [V,C] shadow of the feature-major field
-    _check(_lib.tn_interpolate_values(dev.index, D, N, Cdim, V, vertex_indices.data_ptr(), barycentric_coordinates.data_ptr(),
-                                      field.data_ptr(), out.data_ptr(), scratch.data_ptr(), _stream(dev)))
+    shadow = _field_shadow(field)
+    _check(_lib.tn_interpolate_values_shadow(dev.index, D, N, Cdim, V, vertex_indices.data_ptr(), barycentric_coordinates.data_ptr(),
+                                             shadow.data_ptr(), out.data_ptr(), _stream(dev)))
     return out
+
+
+_SHADOW = {}  # device -> (key, [V,C] shadow): one entry per device, rebuilt when the field's storage, shape or version changes
+
+
+def _field_shadow(field: torch.Tensor) -> torch.Tensor:
+    """[V,C] row-major shadow of the feature-major field, cached by (storage, shape, version): the two interpolations of a
+    training step (coarse + fine pass) and repeated evaluation calls share one transposition."""
+    dev = field.device
+    key = (field.data_ptr(), tuple(field.shape), field._version)
+    hit = _SHADOW.get(dev)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    Cdim, V = field.size(0), field.size(-1)
+    shadow = hit[1] if hit is not None and hit[1].shape == (V, Cdim) else torch.empty((V, Cdim), dtype=torch.float32, device=dev)
+    _check(_lib.tn_make_field_shadow(dev.index, Cdim, V, field.data_ptr(), shadow.data_ptr(), _stream(dev)))
+    _SHADOW[dev] = (key, shadow)
+    return shadow
 
 
 # ---- interpolate_values_backward (py_binding.cpp:341-372) -------------------------------------------
