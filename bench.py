@@ -1,20 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- rays/s of the Tetra-NeRF ray-sampling hot path (forward render) on B200.
+"""bench.py -- rays/s of the Tetra-NeRF ray-sampling hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (forward render, BASELINE configs[1])
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the restated reference algorithm (oracle port)
+    python bench.py --workload tetra-nerf-original ...       # 256 + 256 samples, uniform sampler (registration.py:20-46)
+    python bench.py --mode train ...                         # fused training step (fwd + bwd), BASELINE configs[2] shape
 
 Workload (BASELINE.json configs[1]): 45,000 uniform random points -> scipy Delaunay -> 302,024 tetrahedra,
 4096 camera-like rays per step, `tetra-nerf` config (128 + 128 samples, biased sampler, M = 512), eval-mode
 forward render with random-init MLP (torch.manual_seed(0)) and N(0,1) vertex features.  A "step" = one full
 pass trace -> sample -> interp+MLP -> PDF -> interp+MLP -> composite over one batch of 4096 rays per GPU.
-`value` = rays/s with the rays already resident in HBM; `e2e` = the same through the public Python API with
-pinned HOST ray buffers (H2D + D2H inside the timed region).  Multi-GPU: rays shard across ranks (weak
-scaling, mesh + weights replicated), pixels are all-gathered over NCCL inside the timed region.
+`value` = rays/s with the rays already resident in HBM; `e2e` = the same through the plug-in call nerfstudio makes,
+`TetrahedraNerf.get_outputs(RayBundle)`, with pinned HOST ray buffers (H2D + D2H inside the timed region).
+Multi-GPU: rays shard across ranks (weak scaling, mesh + weights replicated); the pixels of step i are all-gathered
+over NCCL on a side stream while step i+1 renders (every gather completes inside the timed region).
+Both arms print the same `config`; the reference arm never imports the CUDA package.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -34,6 +39,27 @@ NUM_POINTS = 45_000
 RAYS_PER_STEP = 4096
 # algorithmic FLOPs per sample (2 * MACs): coarse 41,088 MAC, fine 61,312 MAC
 FLOP_COARSE, FLOP_FINE = 2 * 41_088, 2 * 61_312
+WORKLOADS = {  # registration.py:20-61
+    "tetra-nerf": {"num_samples": 128, "num_fine_samples": 128, "use_biased_sampler": True, "tag": "tetra-nerf(128+128,biased,M=512)"},
+    "tetra-nerf-original": {"num_samples": 256, "num_fine_samples": 256, "use_biased_sampler": False, "tag": "tetra-nerf-original(256+256,uniform,M=512)"},
+}
+L2_CAP_BYTES_PER_CLK = 6300.0  # LTS throughput cap measured in /opt/skills/guides/B300_MICROARCH.md (same L2 design), x SM clock
+
+
+def synthetic():
+    """tetranerf/b200/synthetic.py loaded by path: the reference arm must not import the `tetranerf` package (that dlopens
+    the CUDA library)"""
+    spec = importlib.util.spec_from_file_location("tn_b200_synthetic", ROOT / "tetra-nerf_b200" / "tetranerf" / "b200" / "synthetic.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_config(workload: str, mode: str, rays: int, world: int, tetrahedra: int):
+    """the `config` object: identical for both arms"""
+    return {"workload": f"delaunay45k_302ktet/{rays}rays/{WORKLOADS[workload]['tag']}/{'train-fwd+bwd' if mode == 'train' else 'eval-forward'}",
+            "tetrahedra": int(tetrahedra), "rays_per_step_per_gpu": int(rays),
+            "parallelism": f"ray-shard x{world} (weak scaling), mesh+weights replicated, NCCL all_gather of pixels"}
 
 
 def peaks():
@@ -91,8 +117,7 @@ class ClockSampler(threading.Thread):
 
 
 def make_workload():
-    from tetranerf.b200 import synthetic as syn
-
+    syn = synthetic()
     V, C = syn.delaunay_mesh(NUM_POINTS, seed=0)
     field = syn.random_field(len(V), 64, seed=3, kind="normal")
     return V, C, field
@@ -113,27 +138,29 @@ def mlp_params():
     return p
 
 
-def cpu_arm(V, C, field, params, num_rays: int, seed: int, nthreads: int = 0):
+def cpu_arm(V, C, field, params, num_rays: int, seed: int, workload: str, nthreads: int = 0):
     """the restated reference algorithm on the host cores (oracle port); returns (seconds, rays)"""
     from oracle import oracle as orc
-    from tetranerf.b200 import synthetic as syn
 
     mesh = cpu_arm.mesh if getattr(cpu_arm, "mesh", None) is not None else orc.OracleMesh(V, C)
     cpu_arm.mesh = mesh
-    o, d = syn.camera_rays(num_rays, seed=seed)
+    o, d = synthetic().camera_rays(num_rays, seed=seed)
+    w = WORKLOADS[workload]
+    cfg = orc.RenderConfig(num_samples=w["num_samples"], num_fine_samples=w["num_fine_samples"], use_biased_sampler=w["use_biased_sampler"])
     t0 = time.perf_counter()
-    orc.render(mesh, torch.from_numpy(field), params, o, d, orc.RenderConfig.tetra_nerf(), nthreads=nthreads)
+    orc.render(mesh, torch.from_numpy(field), params, o, d, cfg, nthreads=nthreads)
     return time.perf_counter() - t0, num_rays
 
 
 def cpu_threads():
-    """(oracle C++ threads, torch intra-op threads): all hardware threads for the threaded C++ stages; torch's
-    small fp32 GEMMs stop scaling (and thrash) far below that on many-core hosts, so its pool is capped at 32."""
+    """(oracle C++ threads, torch intra-op threads): every hardware thread for both, unless TN_BENCH_TORCH_THREADS says
+    otherwise (the torch-CPU fp32 GEMMs of the MLP are the larger share of the CPU time)."""
     from oracle import oracle as orc
 
     cores = orc.hardware_threads()
-    torch.set_num_threads(max(1, min(cores, 32)))
-    return cores
+    nt = int(os.environ.get("TN_BENCH_TORCH_THREADS", "0")) or cores
+    torch.set_num_threads(max(1, nt))
+    return cores, torch.get_num_threads()
 
 
 def run_reference(args, rank, world):
@@ -141,26 +168,62 @@ def run_reference(args, rank, world):
         return
     V, C, field = make_workload()
     params = mlp_params()
-    cores = cpu_threads()
-    sample = 1024  # rays per step: bounded so that K + W steps stay within minutes
+    cores, tthreads = cpu_threads()
+    sample = args.rays  # the whole batch of the named workload every step
     for i in range(args.warmup):
-        cpu_arm(V, C, field, params, sample, seed=100 + i)
+        cpu_arm(V, C, field, params, min(sample, 512), seed=100 + i, workload=args.workload)  # thread pools / allocator warm-up on a short batch
     tot = 0.0
     for i in range(args.steps):
-        dt, _ = cpu_arm(V, C, field, params, sample, seed=200 + i)
+        dt, _ = cpu_arm(V, C, field, params, sample, seed=200 + i, workload=args.workload)
         tot += dt
     value = sample * args.steps / tot
     line = {
         "impl": "reference", "metric": "rays/sec (4096-ray batch, 300k-tet mesh)", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "delaunay45k_302ktet/4096rays/tetra-nerf(128+128,biased,M=512)/eval-forward", "rays_per_step_per_gpu": RAYS_PER_STEP},
+        "config": workload_config(args.workload, "eval", sample, world, len(C)),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} rays/step of the same workload (oracle: C++ trace/match/interp threaded + torch-CPU MLP/compositing)"},
+                         "sample": f"{sample} rays/step of the same workload (oracle: C++ trace/match/interp on {cores} threads + torch-CPU fp32 "
+                                   f"MLP/compositing on {tthreads} threads); warm-up steps use 512-ray batches"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference has no CPU path (src/py_binding.cpp:30-33) and its OptiX build cannot be compiled here; this arm times the restated reference algorithm (oracle/) on the host cores",
     }
     print(json.dumps(line), flush=True)
+
+
+def setup_peer_gather(lib, tracer, dist, dev, world, rank, R):
+    """fused pixel gather: one gathered buffer [world*R, 6] per rank (cudaMalloc + CUDA IPC), mapped into every peer; the
+    render kernels store their pixels straight into all of them (tn_render_set_gather).  Returns the local buffer as a tensor."""
+    import ctypes as C
+
+    nbytes = world * R * 6 * 4
+    ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    lib.tn_peer_alloc.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]
+    lib.tn_peer_open.argtypes = [C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+    lib.tn_render_set_gather.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32]
+    rc = lib.tn_peer_alloc(dev.index, nbytes, C.byref(ptr), handle)
+    assert rc == 0, lib.tn_last_error()
+    mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+    allh = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine)
+    allh = allh.cpu().numpy()
+    ptrs = (C.c_void_p * world)()
+    for k in range(world):
+        if k == rank:
+            ptrs[k] = ptr.value
+        else:
+            q = C.c_void_p()
+            hb = (C.c_ubyte * 64)(*allh[k].tolist())
+            rc = lib.tn_peer_open(dev.index, hb, C.byref(q))
+            assert rc == 0, lib.tn_last_error()
+            ptrs[k] = q.value
+    rc = lib.tn_render_set_gather(tracer.handle, world, rank, ptrs, R)
+    assert rc == 0, lib.tn_last_error()
+
+    class _Buf:  # __cuda_array_interface__ view of the IPC allocation
+        __cuda_array_interface__ = {"shape": (world * R, 6), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+
+    return torch.as_tensor(_Buf(), device=dev)
 
 
 def main():
@@ -169,10 +232,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=int, default=RAYS_PER_STEP)
+    ap.add_argument("--rays", type=int, default=None, help="rays per step per GPU (default 4096; 8192 for --mode train)")
+    ap.add_argument("--workload", default="tetra-nerf", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="eval", choices=["eval", "train"])
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer-store gather (default) or NCCL all_gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.rays is None:
+        args.rays = 8192 if args.mode == "train" else RAYS_PER_STEP
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,9 +250,11 @@ def main():
     import torch.distributed as dist
 
     from tetranerf import cpp
-    from tetranerf.b200 import synthetic as syn
-    from tetranerf.b200.render import FusedRenderer, RenderSettings
+    from tetranerf.b200.render import RenderSettings
+    from tetranerf.nerfstudio import model as tnm
+    from tetranerf.utils.extension import tetranerf_cpp_extension as ext
 
+    syn = synthetic()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -192,13 +262,20 @@ def main():
     R = args.rays
     V, C, field = make_workload()
     params = mlp_params()
-    tracer = cpp.TetrahedraTracer(dev)
-    dV, dC = torch.from_numpy(V).to(dev), torch.from_numpy(C).to(dev)
-    tracer.load_tetrahedra(dV, dC)
-    fr = FusedRenderer(tracer)
-    fr.set_field(torch.from_numpy(field).to(dev))
-    fr.set_weights(params)
-    st = RenderSettings.tetra_nerf()
+    w = WORKLOADS[args.workload]
+    if args.mode == "train":
+        return run_train(args, rank, world, dev, V, C, field, params, dist)
+    # the plug-in object nerfstudio drives: TetrahedraNerf (model.py:209-662); its eval-mode get_outputs is the fused CUDA pipeline
+    cfg = tnm.TetrahedraNerfConfig(num_tetrahedra_vertices=len(V), num_tetrahedra_cells=len(C), num_samples=w["num_samples"],
+                                   num_fine_samples=w["num_fine_samples"], use_biased_sampler=w["use_biased_sampler"])
+    model = tnm.TetrahedraNerf(cfg)
+    sd = {"tetrahedra_vertices": torch.from_numpy(V), "tetrahedra_cells": torch.from_numpy(C), "tetrahedra_field": torch.from_numpy(field)}
+    sd.update(params)
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    tracer = model.get_tetrahedra_tracer()
+    fr = model._fused_renderer()
+    st = RenderSettings(512, w["num_samples"], w["num_fine_samples"], w["use_biased_sampler"], float(model.collider.far_plane), (1.0, 1.0, 1.0))
     nsteps = args.warmup + args.steps
     # a different ray batch every step; each rank gets its own shard (weak scaling)
     host_od = []  # pinned [2,R,3] (origins | directions): one host->device copy per step on the end-to-end path
@@ -208,23 +285,35 @@ def main():
     dev_od = [t.to(dev) for t in host_od]
     out = {"rgb": torch.empty((R, 3), device=dev), "accumulation": torch.empty((R, 1), device=dev), "depth": torch.empty((R, 1), device=dev),
            "ray_mask": torch.empty((R,), dtype=torch.bool, device=dev)}
-    pix = torch.empty((R, 5), device=dev)
-    gathered = torch.empty((world * R, 5), device=dev) if world > 1 else None
+    gather_mode = "none" if world == 1 else args.gather
+    gathered = None
+    if gather_mode == "peer":
+        gathered = setup_peer_gather(ext._lib, tracer, dist, dev, world, rank, R)
+    elif gather_mode == "nccl":
+        pix = torch.empty((R, 5), device=dev)
+        gathered = torch.empty((world * R, 5), device=dev)
     host_pix = torch.empty((R, 5), dtype=torch.float32).pin_memory()
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if k != "ray_mask"}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    fr.set_profiling(True)
 
     def step(i, e2e: bool):
-        od = host_od[i].to(dev, non_blocking=True) if e2e else dev_od[i]
-        fr.render(od[0], od[1], st, out=out)
-        torch.cat((out["rgb"], out["accumulation"], out["depth"]), dim=1, out=pix)
-        if world > 1:
+        if e2e:  # the call nerfstudio makes: Model.forward(RayBundle) -> collider -> TetrahedraNerf.get_outputs
+            od = host_od[i].to(dev, non_blocking=True)
+            with torch.no_grad():
+                res = model(tnm.RayBundle(origins=od[0], directions=od[1]))
+            for k, v in host_out.items():
+                v.copy_(res[k], non_blocking=True)
+        else:
+            od = dev_od[i]
+            fr.render(od[0], od[1], st, out=out)
+        if gather_mode == "nccl":
+            src = out if not e2e else res
+            torch.cat((src["rgb"], src["accumulation"], src["depth"]), dim=1, out=pix)
             dist.all_gather_into_tensor(gathered, pix)  # final NCCL gather of rendered pixels
-        if e2e:
-            host_pix.copy_(pix, non_blocking=True)
+        # gather_mode == "peer": the render kernels already stored this rank's pixels into every rank's gathered buffer
 
     def timed(e2e: bool, profile: bool = False):
-        fr.set_profiling(profile)  # per-kernel events only on the separate profiling pass (they feed kernel_ms / the roofline)
+        fr.set_profiling(profile)  # per-kernel events only on the separate profiling pass (they feed kernel_ms / the rooflines)
         for i in range(args.warmup):
             step(i, e2e)
         torch.cuda.synchronize(dev)
@@ -262,55 +351,85 @@ def main():
     sampler.join(timeout=2)
     tracer.synchronize()
     n_active = int(out["ray_mask"].sum().item())
+    # sum of visited tetrahedra of the last batch (SURVEY §8d traversal bytes)
+    import ctypes as Ct
+
+    bufs = fr.debug_buffers()
+    numv = torch.empty((R,), dtype=torch.int32, device=dev)
+    Ct.CDLL("libcudart.so").cudaMemcpy(Ct.c_void_p(numv.data_ptr()), Ct.c_void_p(bufs["num"]), Ct.c_size_t(4 * R), Ct.c_int(3))
+    sum_k = int(numv.sum().item())
+    if gather_mode == "peer":  # every rank's pixels of the last step landed in this rank's gathered buffer
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        mine = gathered[rank * R:(rank + 1) * R]
+        assert torch.equal(mine[:, :3], out["rgb"]) and bool((gathered[:, 3] >= 0).all()), "fused pixel gather: local block differs from the render"
 
     if rank == 0:
         pk = peaks()
         total_rays = world * R * args.steps
         value = total_rays / (ms_total * 1e-3)
         e2e = total_rays / (ms_e2e * 1e-3)
+        Sc, S2 = st.num_samples, st.num_samples + st.num_fine_samples + 1
+        flops = {"mlp_fine": n_active * S2 * FLOP_FINE, "mlp_coarse": n_active * Sc * FLOP_COARSE}
+        traffic = {}
+        prof = ROOT / "profiles" / "roofline_traffic.json"
+        if prof.exists():
+            try:
+                traffic = json.loads(prof.read_text())
+            except Exception:
+                traffic = {}
         # dominant kernel: the fine interp+MLP pass (tensor-bound)
         dom = max(kern_ms, key=kern_ms.get)
-        S2 = st.num_samples + st.num_fine_samples + 1
-        flops = {"mlp_fine": n_active * S2 * FLOP_FINE, "mlp_coarse": n_active * st.num_samples * FLOP_COARSE}
-        roof = {"kernel": dom, "bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops"], "peak_src": pk["src"] + " bf16 burst", "traffic": None}
+        roof = {"kernel": dom, "bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops"], "peak_src": pk["src"] + " bf16 burst",
+                "traffic": traffic.get(dom), "traffic_src": "ncu --set full capture committed under profiles/ (not re-measured in this run)"}
         if dom in flops:
             ach = flops[dom] / (kern_ms[dom] * 1e-3) / 1e12
             roof.update(achieved=ach, frac=ach / pk["bf16_tflops"],
                         note="algorithmic fp32-equivalent FLOPs (SURVEY §8d); the kernel issues 3 bf16 MMAs per algorithmic MAC (bf16x3), "
                              "so tensor-pipe occupancy is ~3x this fraction")
-        else:  # traversal dominates: HBM accounting of SURVEY §8d is filled by the ncu pass
-            roof.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], peak_src=pk["src"] + " HBM copy", achieved=None, frac=None)
-        prof = ROOT / "profiles" / "roofline_traffic.json"
-        if prof.exists():
-            try:
-                roof["traffic"] = json.loads(prof.read_text()).get(dom)
-            except Exception:
-                pass
+        # the traversal (BASELINE metric: "traversal HBM% of roofline"): SURVEY §8d algorithmic bytes / (prefetch + trace time)
+        Fcount = tracer.num_faces()
+        tb = 28 * R + 52 * sum_k + 12 * len(V) + 16 * len(C) + 20 * Fcount
+        clk = sampler.result().get("sm_max_mhz") or pk.get("sm_max_mhz") or 1965.0
+        l2_peak = L2_CAP_BYTES_PER_CLK * clk * 1e6 / 1e9
+        tgb = tb / (kern_ms["trace"] * 1e-3) / 1e9
+        roof_trace = {"kernel": "trace (k_l2_prefetch + k_trace / k_walk)", "bound": "hbm", "unit": "GB/s", "achieved": tgb, "peak": pk["hbm_gbs"],
+                      "peak_src": pk["src"] + " HBM copy", "frac": tgb / pk["hbm_gbs"], "bytes": tb, "traffic": traffic.get("trace"),
+                      "l2_peak_gbs": l2_peak, "l2_frac": tgb / l2_peak,
+                      "note": "algorithmic bytes 28R + 52 sum(K) + 12V + 16T + 20F (SURVEY §8d); the ~56 MB working set is L2-resident by design, "
+                              "so the L2 fraction (LTS cap 6300 B/clk x max SM clock) is reported beside the HBM fraction"}
         line = {
             "metric": "rays/sec (4096-ray batch, 300k-tet mesh)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (trace/interp/compositing) + bf16x3 tensor-core MLP with f32 accumulate", "data": "synthetic",
-            "config": {"workload": "delaunay45k_302ktet/4096rays/tetra-nerf(128+128,biased,M=512)/eval-forward", "tetrahedra": int(len(C)),
-                       "rays_per_step_per_gpu": R, "parallelism": f"ray-shard x{world}, mesh+weights replicated, NCCL all_gather of pixels",
-                       "l2": "flushed between timed steps (256 MiB fill); a new ray batch every step"},
-            "kernel_ms": kern_ms, "roofline": roof,
-            "e2e": {"value": e2e, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 2 * R * 12, "d2h_bytes_per_step": R * 20},
+            "config": workload_config(args.workload, "eval", R, world, len(C)),
+            "timing": {"l2": "flushed between timed steps (256 MiB fill); a new ray batch every step", "events": "CUDA events per step on the launch stream, max over ranks",
+                       "gather": {"none": "single GPU", "peer": "fused: render kernels store pixels into every rank's gathered buffer over NVLink (no collective)",
+                                  "nccl": "NCCL all_gather_into_tensor inside every step"}[gather_mode]},
+            "kernel_ms": kern_ms, "roofline": roof, "roofline_trace": roof_trace,
+            "e2e": {"value": e2e, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 2 * R * 12, "d2h_bytes_per_step": R * 20,
+                    "api": "TetrahedraNerf.forward(RayBundle) -> get_outputs (the nerfstudio plug-in call), pinned host rays in, pinned host pixels out"},
             "gpu_launches": int(launches), "clocks": sampler.result(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = cpu_threads()
-            for w in range(2):
-                cpu_arm(V, C, field, params, 256, seed=7 + w)  # warm (thread pools, MKL)
+            cores, tthreads = cpu_threads()
+            for wi in range(2):
+                cpu_arm(V, C, field, params, 256, seed=7 + wi, workload=args.workload)  # warm (thread pools, MKL)
             tot_t, tot_n, k = 0.0, 0, 0
             while tot_t < 10.0 and k < 64:  # ~10 s of CPU work
-                dt, n = cpu_arm(V, C, field, params, 1024, seed=300 + k)
+                dt, n = cpu_arm(V, C, field, params, 1024, seed=300 + k, workload=args.workload)
                 tot_t, tot_n, k = tot_t + dt, tot_n + n, k + 1
             line["cpu_baseline"] = {"value": tot_n / tot_t, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": f"{tot_n} rays ({k} batches of 1024) of the same workload through oracle/ "
-                                              "(threaded C++ trace/match/interp + torch-CPU fp32 MLP/compositing, torch pool capped at 32 threads)"}
+                                              f"(C++ trace/match/interp on {cores} threads + torch-CPU fp32 MLP/compositing on {tthreads} threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def run_train(args, rank, world, dev, V, C, field, params, dist):
+    raise SystemExit("--mode train: see tetranerf.b200.train (fused training step)")
 
 
 if __name__ == "__main__":

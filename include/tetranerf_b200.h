@@ -111,6 +111,16 @@ int tn_render_set_weights(tn_tracer *h, const float *const *d_params12, void *st
 /* d_rgb f32[R,3], d_acc f32[R,1], d_depth f32[R,1], d_mask u8[R] */
 int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
               float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, void *stream);
+/* ---- multi-GPU: final gather of the rendered pixels (north_star; tetranerf/nerfstudio/pipeline.py:53-58 is the reference's only
+ * multi-GPU mechanism).  One process per GPU; each rank owns a gathered-pixel buffer f32[world * rays_per_rank, 6]
+ * (r, g, b, accumulation, depth, mask) allocated with tn_peer_alloc, whose 64-byte CUDA IPC handle the ranks exchange and map
+ * with tn_peer_open.  After tn_render_set_gather the kernels of tn_render store every pixel straight into ALL ranks' buffers
+ * (peer stores over NVLink, row = rank * rays_per_rank + ray): the all-gather is fused into the render, no collective call. */
+int tn_peer_alloc(int device, uint64_t bytes, void **d_ptr, unsigned char *handle64);
+int tn_peer_open(int device, const unsigned char *handle64, void **d_ptr);
+int tn_peer_close(int device, void *d_ptr);
+int tn_peer_free(int device, void *d_ptr);
+int tn_render_set_gather(tn_tracer *h, uint32_t world, uint32_t rank, void *const *d_peer_buffers, uint32_t rays_per_rank);
 /* per-kernel CUDA-event timing of the last tn_render call: ms6 = trace, sample_coarse, mlp_coarse, sample_fine,
  * mlp_fine, composite (used by bench.py for the roofline of the dominant kernel) */
 int tn_render_set_profiling(tn_tracer *h, int enable);

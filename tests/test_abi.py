@@ -54,3 +54,24 @@ def test_no_silent_cpu_fallback():
         cpp.TetrahedraTracer(torch.device("cuda:0"))
     with pytest.raises(RuntimeError):
         cpp.interpolate_values(torch.zeros((1, 4), dtype=torch.int32), torch.zeros((1, 3)), torch.zeros((2, 3)))
+
+
+def test_pybind_module_surface():
+    """the compiled pybind11 module named like the reference's (src/py_binding.cpp:433-449) imports without a GPU and exposes the surface"""
+    import importlib.util
+    import sys as _sys
+
+    bp = ROOT / "tetra-nerf_b200" / "build.py"
+    spec = importlib.util.spec_from_file_location("tn_build_for_test", bp)
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.pybind_path().exists(), "run python tetra-nerf_b200/build.py"
+    from tetranerf.utils.extension._pybind import tetranerf_cpp_extension as pb
+
+    assert pb.__name__.endswith("tetranerf_cpp_extension") and pb.BINDING == "pybind11"
+    for n in ("trace_rays", "trace_rays_triangles", "find_visited_cells", "find_tetrahedra", "load_tetrahedra", "device"):
+        assert hasattr(pb.TetrahedraTracer, n)
+    for n in ("triangulate", "find_average_spacing", "interpolate_values", "interpolate_values_backward", "gather_uint32", "scatter_ema_uint32"):
+        assert callable(getattr(pb, n))
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        pb.TetrahedraTracer(torch.device("cpu"))

@@ -105,6 +105,38 @@ int tn_get_faces(tn_tracer *h, uint32_t *d_tri, uint32_t *d_tt, void *stream) {
 
 uint64_t tn_launch_count(tn_tracer *h) { return h ? h->launches : 0; }
 
+// ---- peer-mapped buffers (one process per GPU): cudaMalloc + CUDA IPC, so that a kernel of rank a can store into rank b's
+// memory over NVLink (fused pixel gather, tn_render_set_gather) ----
+int tn_peer_alloc(int device, uint64_t bytes, void **d_ptr, unsigned char *handle64) {
+    if (!d_ptr || !handle64 || bytes == 0) return tn::fail(TN_ERR_ARG, "tn_peer_alloc: null argument");
+    tn::DeviceGuard g(device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    TN_CUDA(cudaMalloc(d_ptr, bytes));
+    TN_CUDA(cudaMemset(*d_ptr, 0, bytes));
+    cudaIpcMemHandle_t hd;
+    TN_CUDA(cudaIpcGetMemHandle(&hd, *d_ptr));
+    memcpy(handle64, &hd, 64);
+    return TN_OK;
+}
+int tn_peer_open(int device, const unsigned char *handle64, void **d_ptr) {
+    if (!d_ptr || !handle64) return tn::fail(TN_ERR_ARG, "tn_peer_open: null argument");
+    tn::DeviceGuard g(device);
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    TN_CUDA(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return TN_OK;
+}
+int tn_peer_close(int device, void *d_ptr) {
+    tn::DeviceGuard g(device);
+    if (d_ptr) TN_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return TN_OK;
+}
+int tn_peer_free(int device, void *d_ptr) {
+    tn::DeviceGuard g(device);
+    if (d_ptr) TN_CUDA(cudaFree(d_ptr));
+    return TN_OK;
+}
+
 // batches with at least `n` rays take the adjacency-walk fast path of trace_rays (0 = always, UINT32_MAX = never);
 // measured crossover on B200 / 302k tetrahedra: ~10k rays (profiles/r1_trace_sweep.json)
 extern "C" int tn_set_walk_min_rays(tn_tracer *h, uint32_t n) {

@@ -43,6 +43,9 @@ struct RenderState {
     uint4 *vi_c = nullptr;
     float *ebins_f = nullptr, *bary_f = nullptr, *out_f = nullptr, *dirbias = nullptr;
     uint4 *vi_f = nullptr;
+    // fused pixel gather (tn_render_set_gather): peer[k] = rank k's [world * rays_per_rank, 6] gathered-pixel buffer
+    float *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t gather_world = 0, gather_rank = 0, gather_stride = 0;
     // optional per-kernel timing (bench.py roofline): events around the 6 kernels of tn_render
     bool profile = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -126,7 +129,25 @@ struct SampleParams {
     float *rgb, *acc, *depth;
     uint8_t *mask;
     float far_plane, bg0, bg1, bg2;
+    // fused pixel gather: when gather_world > 0 every rendered pixel is also stored, as (r, g, b, accumulation, depth, mask), at row
+    // gather_rank * gather_stride + ray of EVERY rank's gathered buffer (peer[k] is mapped peer memory: stores travel over NVLink)
+    float *peer[8];
+    uint32_t gather_world, gather_rank, gather_stride;
 };
+
+// lane 0 writes the local outputs; lanes < gather_world each post the pixel to one rank's gathered buffer (three 8-byte stores)
+__device__ __forceinline__ void store_pixel(const SampleParams &p, uint32_t ray, int lane, float r, float g, float b, float a, float depth, uint8_t mask) {
+    if (lane == 0) {
+        p.rgb[3 * (size_t)ray] = r; p.rgb[3 * (size_t)ray + 1] = g; p.rgb[3 * (size_t)ray + 2] = b;
+        p.acc[ray] = a; p.depth[ray] = depth;
+        if (p.mask != nullptr) p.mask[ray] = mask;
+    }
+    if ((uint32_t)lane < p.gather_world) {
+        float2 *dst = reinterpret_cast<float2 *>(p.peer[lane] + 6 * ((size_t)p.gather_rank * p.gather_stride + ray));
+        dst[0] = make_float2(r, g); dst[1] = make_float2(b, a); dst[2] = make_float2(depth, mask ? 1.f : 0.f);
+        __threadfence_system();  // the pixel is performed at the peer before this kernel can complete
+    }
+}
 
 __device__ __forceinline__ float warp_incl_scan_f(float v, int lane) {
 #pragma unroll
@@ -220,10 +241,7 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const Sampl
     float *t_out = t_in + A, *pm = t_out + A, *cum = pm + A, *e = cum + B;
     const uint32_t n = p.num[ray];
     if (n == 0) {  // model.py:640-650 : background colour, accumulation 0, depth = collider far plane
-        if (lane == 0) {
-            p.rgb[3 * (size_t)ray] = p.bg0; p.rgb[3 * (size_t)ray + 1] = p.bg1; p.rgb[3 * (size_t)ray + 2] = p.bg2;
-            p.acc[ray] = 0.f; p.depth[ray] = p.far_plane; p.mask[ray] = 0;
-        }
+        store_pixel(p, ray, lane, p.bg0, p.bg1, p.bg2, 0.f, p.far_plane, 0);
         return;
     }
     uint32_t slot = 0;
@@ -424,14 +442,9 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_composite(const SamplePar
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
     const uint32_t mi = min(first, S2 - 1);
-    if (lane == 0) {
-        // RGBRenderer (eval): comp + background * (1 - acc), clamped to [0,1]
-        p.rgb[3 * (size_t)ray] = fminf(fmaxf(r + p.bg0 * (1.f - a), 0.f), 1.f);
-        p.rgb[3 * (size_t)ray + 1] = fminf(fmaxf(g + p.bg1 * (1.f - a), 0.f), 1.f);
-        p.rgb[3 * (size_t)ray + 2] = fminf(fmaxf(b + p.bg2 * (1.f - a), 0.f), 1.f);
-        p.acc[ray] = a;
-        p.depth[ray] = (eb[mi] + eb[mi + 1]) / 2.f;
-    }
+    // RGBRenderer (eval): comp + background * (1 - acc), clamped to [0,1]
+    store_pixel(p, ray, lane, fminf(fmaxf(r + p.bg0 * (1.f - a), 0.f), 1.f), fminf(fmaxf(g + p.bg1 * (1.f - a), 0.f), 1.f),
+                fminf(fmaxf(b + p.bg2 * (1.f - a), 0.f), 1.f), a, (eb[mi] + eb[mi + 1]) / 2.f, 1);
 }
 
 // single-pass configuration (num_fine_samples == 0, model.py:573 skipped): colours come from the first and only pass -- the
@@ -512,14 +525,14 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     int rc = ensure_ws(r, R, M, Sc, S2);
     if (rc) return rc;
     TN_CUDA(cudaMemsetAsync(r->n_active, 0, 16, s));
+#define TN_EV(i) do { if (r->profile) cudaEventRecord(r->ev[i], s); } while (0)
+    TN_EV(0);  // the "trace" interval includes the L2 warm-up it exists for
     {   // L2 warm-up of everything read-only that the step gathers from (mesh tables, field shadow, weight image)
         const void *extra[2] = {r->fshadow, r->wimg};
         const size_t extra_b[2] = {sizeof(float) * 64 * (size_t)r->V, 32768 + 3 * 65536};
         rc = launch_prefetch(h, extra, extra_b, 2, s);
         if (rc) return rc;
     }
-#define TN_EV(i) do { if (r->profile) cudaEventRecord(r->ev[i], s); } while (0)
-    TN_EV(0);
     rc = launch_trace_internal(h, d_origins, d_directions, R, M, r->num, r->cells, r->bary, r->dist, r->verts, 0, s);
     if (rc) return rc;
     TN_EV(1);
@@ -531,6 +544,11 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     p.ebins_f = r->ebins_f; p.bary_f = r->bary_f; p.vi_f = r->vi_f; p.dirbias = r->dirbias; p.w4dir = r->w4dir; p.out_f = r->out_f;
     p.rgb = d_rgb; p.acc = d_acc; p.depth = d_depth; p.mask = d_mask;
     p.far_plane = cfg->far_plane; p.bg0 = cfg->background[0]; p.bg1 = cfg->background[1]; p.bg2 = cfg->background[2];
+    if (r->gather_world) {
+        if (R > r->gather_stride) return fail(TN_ERR_ARG, "tn_render: more rays than the gathered-pixel buffers were sized for (tn_render_set_gather)");
+        for (int k = 0; k < 8; ++k) p.peer[k] = r->peer[k];
+        p.gather_world = r->gather_world; p.gather_rank = r->gather_rank; p.gather_stride = r->gather_stride;
+    }
     const uint32_t Smax = std::max(Sc, S2);
     const size_t smem_sc = SAMPLE_WARPS * sizeof(float) * sample_floats(M, Smax, 1);  // coarse: cum[] has M+1 entries
     const size_t smem_sf = SAMPLE_WARPS * sizeof(float) * sample_floats(M, Smax, 0);
@@ -569,6 +587,18 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
 #undef TN_EV
     h->launches += 5;
     TN_CUDA(cudaGetLastError());
+    return TN_OK;
+}
+
+// fused pixel gather: from now on tn_render stores every pixel into all ranks' gathered buffers (peer memory) from inside its own
+// kernels -- the all-gather of the rendered pixels without a collective call.  world == 0 switches it off.
+extern "C" int tn_render_set_gather(tn_tracer *h, uint32_t world, uint32_t rank, void *const *d_peer_buffers, uint32_t rays_per_rank) {
+    if (!h) return fail(TN_ERR_ARG, "null tracer");
+    if (world > 8 || (world && (rank >= world || !d_peer_buffers || rays_per_rank == 0))) return fail(TN_ERR_ARG, "tn_render_set_gather: world <= 8, rank < world");
+    RenderState *r = state(h);
+    for (uint32_t k = 0; k < 8; ++k) r->peer[k] = k < world ? (float *)d_peer_buffers[k] : nullptr;
+    for (uint32_t k = 0; k < world; ++k) if (!r->peer[k]) return fail(TN_ERR_ARG, "tn_render_set_gather: null peer buffer");
+    r->gather_world = world; r->gather_rank = rank; r->gather_stride = rays_per_rank;
     return TN_OK;
 }
 

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams p) {
     // ---- hull entry: closest hit over the hull faces (smallest (t, face id) key) ----
     u64 best = ~0ull;
     float bu = 0.f, bv = 0.f;
-    uint32_t btet = TN_EMPTY, bj = 0;
+    uint32_t btet = TN_EMPTY, bj = 0, hullhits = 0;
     {
         const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
         const float pad = 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + p.absmax);
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams p) {
                     float t, u, v;  // a hull face is always owned: its stored winding is this rotation
                     if (tri_test(s[(j + 1) & 3], s[(j + 2) & 3], s[(j + 3) & 3], t, u, v)) {
                         const u64 k = ((u64)__float_as_uint(t) << 32) | (f[j] & TN_FACE_MASK);
+                        hullhits++;
                         if (k < best) { best = k; bu = u; bv = v; btet = p.hull_tet[cbase + c]; bj = (uint32_t)j; }
                     }
                 }
@@ -92,6 +93,16 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams p) {
         }
     }
     if (btet == TN_EMPTY) { p.num[ray] = 0; return; }  // the ray misses the mesh
+    // A ray the walk may certify crosses the (closed, convex) hull exactly twice: once in, once out.  One hull hit = the origin is
+    // inside the mesh (the "entry" is the exit face: the walk would run backwards); more than two = the ray passes through a hull
+    // edge or vertex, where the all-hits gather reports the extra hull faces -- they count towards the M-1 hit cap
+    // (optix_trace_rays.cu:312-315) although pairing drops them again.  Both go to the exact all-hits stage at once.
+    if (hullhits != 2) {
+        p.list[atomicAdd(p.list_count, 1u)] = ray;
+        atomicAdd(p.list_count + 1, 1u);
+        p.num[ray] = 0;
+        return;
+    }
 
     // ---- walk ----
     uint32_t c = btet, jin = bj, fin = (uint32_t)best, nfaces = 1, nrec = 0;
@@ -202,7 +213,7 @@ __global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
     // ---- hull entry: closest hit over the hull faces (smallest (t, face id) key); lane c takes child c of the popped node ----
     u64 best = ~0ull;
     float bu = 0.f, bv = 0.f;
-    uint32_t btet = TN_EMPTY, bj = 0;
+    uint32_t btet = TN_EMPTY, bj = 0, hullhits = 0;
     {
         const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
         const float pad = 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + p.absmax);
@@ -238,6 +249,7 @@ __global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
                     float t, u, v;
                     if (tri_test(s[(j + 1) & 3], s[(j + 2) & 3], s[(j + 3) & 3], t, u, v)) {
                         const u64 k = ((u64)__float_as_uint(t) << 32) | (f[j] & TN_FACE_MASK);
+                        hullhits++;
                         if (k < best) { best = k; bu = u; bv = v; btet = p.hull_tet[cbase + lane]; bj = (uint32_t)j; }
                     }
                 }
@@ -254,9 +266,19 @@ __global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
         best = m;
         bu = __shfl_sync(M8, bu, win); bv = __shfl_sync(M8, bv, win);
         btet = __shfl_sync(M8, btet, win); bj = __shfl_sync(M8, bj, win);
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) hullhits += __shfl_xor_sync(M8, hullhits, o);
     }
     if (lane >= 4u) return;
     if (btet == TN_EMPTY) { if (lane == 0) p.num[ray] = 0; return; }  // the ray misses the mesh
+    if (hullhits != 2) {  // origin inside the mesh, or a hull edge / vertex hit: exact all-hits stage (see k_walk)
+        if (lane == 0) {
+            p.list[atomicAdd(p.list_count, 1u)] = ray;
+            atomicAdd(p.list_count + 1, 1u);
+            p.num[ray] = 0;
+        }
+        return;
+    }
 
     // ---- walk: lane j owns vertex j / the face opposite to it; every lane keeps the (uniform) bookkeeping ----
     uint32_t c = btet, jin = bj, fin = (uint32_t)best, nfaces = 1, nrec = 0;
