@@ -153,12 +153,13 @@ def cpu_arm(V, C, field, params, num_rays: int, seed: int, workload: str, nthrea
 
 
 def cpu_threads():
-    """(oracle C++ threads, torch intra-op threads): every hardware thread for both, unless TN_BENCH_TORCH_THREADS says
-    otherwise (the torch-CPU fp32 GEMMs of the MLP are the larger share of the CPU time)."""
+    """(oracle C++ threads, torch intra-op threads).  The C++ stages use every hardware thread; torch's fp32 GEMMs of the MLP are
+    capped at 32 threads -- measured on the 128-thread host of the B200 box (profiles/r2_cpu_threads.json): 16 -> 1683, 32 -> 1918,
+    64 -> 1485, 128 -> 224 rays/s.  TN_BENCH_TORCH_THREADS overrides."""
     from oracle import oracle as orc
 
     cores = orc.hardware_threads()
-    nt = int(os.environ.get("TN_BENCH_TORCH_THREADS", "0")) or cores
+    nt = int(os.environ.get("TN_BENCH_TORCH_THREADS", "0")) or min(cores, 32)
     torch.set_num_threads(max(1, nt))
     return cores, torch.get_num_threads()
 

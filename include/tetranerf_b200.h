@@ -111,6 +111,19 @@ int tn_render_set_weights(tn_tracer *h, const float *const *d_params12, void *st
 /* d_rgb f32[R,3], d_acc f32[R,1], d_depth f32[R,1], d_mask u8[R] */
 int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
               float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, void *stream);
+/* ---- fused training step: TetrahedraNerf.get_outputs in training mode (model.py:520-662) + its autograd backward.
+ * Forward = the fused pipeline with the stratified bins of training (model.py:169-174 for the coarse pass, PDFSampler train_stratified
+ * for the fine pass; the uniform [0,1) draws come from the caller, d_jitter_coarse f32[R,S_c+1] / d_jitter_fine f32[R,S_f+1] indexed by
+ * ray, NULL = the eval-mode bins) and the training-mode RGBRenderer (no nan_to_num, no clamp).  Backward continues from the buffers of
+ * the LAST training forward: d_grad_rgb f32[R,3] (+ optional d_grad_acc f32[R]) -> d_grad_field f32[64,V] (interpolate_values_backward,
+ * src/tetrahedra_tracer.cu:223-248) and the twelve MLP gradients in the order / layouts of tn_render_set_weights; use_gradient_scaling =
+ * GradientScaler (model.py:195-205,625-630).  Every output element is written.  The MLP backward runs on tcgen05 (recompute + dX + dW
+ * GEMMs per 128-sample tile, weight gradients resident in TMEM); no [samples,128] tensor is materialised in HBM. */
+int tn_render_train_forward(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
+                            const float *d_jitter_coarse, const float *d_jitter_fine, float *d_rgb, float *d_acc, float *d_depth,
+                            uint8_t *d_mask, void *stream);
+int tn_render_train_backward(tn_tracer *h, const float *d_grad_rgb, const float *d_grad_acc, int use_gradient_scaling, float *d_grad_field,
+                             float *const *d_grad_params12, void *stream);
 /* ---- multi-GPU: final gather of the rendered pixels (north_star; tetranerf/nerfstudio/pipeline.py:53-58 is the reference's only
  * multi-GPU mechanism).  One process per GPU; each rank owns a gathered-pixel buffer f32[world * rays_per_rank, 6]
  * (r, g, b, accumulation, depth, mask) allocated with tn_peer_alloc, whose 64-byte CUDA IPC handle the ranks exchange and map

@@ -338,11 +338,18 @@ def map_from_real_distances_to_biased_with_bounds(num_bounds, bounds, samples):
     return torch.gather(cum_lengths, 1, intervals) + torch.gather(lengths, 1, intervals) * rest
 
 
-def coarse_bins(cfg: RenderConfig, nears, fars, num_visited, hit_distances):
-    """Eval-mode (no jitter) TetrahedraSampler.generate_ray_samples (model.py:141-192) or nerfstudio
-    UniformSampler.  Returns (euclidean_bins [R,S+1], spacing_bins [R,S+1])."""
+def coarse_bins(cfg: RenderConfig, nears, fars, num_visited, hit_distances, t_rand=None):
+    """TetrahedraSampler.generate_ray_samples (model.py:141-192) or nerfstudio UniformSampler.  t_rand = None: eval mode (no
+    jitter); t_rand f32[R,S+1] uniform in [0,1): the stratified training bins (model.py:169-174 -- the reference draws it with
+    torch.rand; here it is an input so that kernel and oracle consume the same numbers).
+    Returns (euclidean_bins [R,S+1], spacing_bins [R,S+1])."""
     S = cfg.num_samples
     bins = torch.linspace(0.0, 1.0, S + 1)[None, ...]
+    if t_rand is not None:
+        bin_centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+        bin_upper = torch.cat([bin_centers, bins[..., -1:]], -1)
+        bin_lower = torch.cat([bins[..., :1], bin_centers], -1)
+        bins = bin_lower + (bin_upper - bin_lower) * t_rand
     euclid = bins * fars + (1 - bins) * nears
     if cfg.use_biased_sampler:
         euclid = map_from_real_distances_to_biased_with_bounds(num_visited.long(), hit_distances, euclid)
@@ -352,9 +359,10 @@ def coarse_bins(cfg: RenderConfig, nears, fars, num_visited, hit_distances):
     return euclid, bins
 
 
-def pdf_bins(cfg: RenderConfig, spacing_bins, weights, nears, fars, histogram_padding=0.01, eps=1e-5):
-    """Eval-mode PDFSampler.generate_ray_samples(include_original=True) (nerfstudio 0.3.x
-    model_components/ray_samplers.py).  weights [R,S,1].  Returns (euclidean_bins, spacing_bins) [R,S+Sf+2]."""
+def pdf_bins(cfg: RenderConfig, spacing_bins, weights, nears, fars, histogram_padding=0.01, eps=1e-5, u_rand=None):
+    """PDFSampler.generate_ray_samples(include_original=True) (nerfstudio 0.3.x model_components/ray_samplers.py).
+    weights [R,S,1].  u_rand = None: eval mode (bin mid-points); u_rand f32[R,Sf+1] uniform in [0,1): train_stratified
+    (u = linspace + rand / num_bins).  Returns (euclidean_bins, spacing_bins) [R,S+Sf+2], detached like upstream."""
     num_bins = cfg.num_fine_samples + 1
     w = weights[..., 0] + histogram_padding
     weights_sum = torch.sum(w, dim=-1, keepdim=True)
@@ -365,8 +373,11 @@ def pdf_bins(cfg: RenderConfig, spacing_bins, weights, nears, fars, histogram_pa
     cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
     u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins)
-    u = u + 1.0 / (2 * num_bins)
-    u = u.expand(size=(*cdf.shape[:-1], num_bins)).contiguous()
+    if u_rand is not None:
+        u = u.expand(size=(*cdf.shape[:-1], num_bins)) + u_rand / num_bins
+    else:
+        u = (u + 1.0 / (2 * num_bins)).expand(size=(*cdf.shape[:-1], num_bins))
+    u = u.contiguous()
     existing_bins = spacing_bins
     inds = torch.searchsorted(cdf, u, side="right")
     below = torch.clamp(inds - 1, 0, existing_bins.shape[-1] - 1)
@@ -378,6 +389,7 @@ def pdf_bins(cfg: RenderConfig, spacing_bins, weights, nears, fars, histogram_pa
     t = torch.clip(torch.nan_to_num((u - cdf_g0) / (cdf_g1 - cdf_g0), 0), 0, 1)
     bins = bins_g0 + t * (bins_g1 - bins_g0)
     bins, _ = torch.sort(torch.cat([existing_bins, bins], -1), -1)
+    bins = bins.detach()  # "Stop gradients"
     euclid = bins * fars + (1 - bins) * nears
     return euclid, bins
 
@@ -445,3 +457,96 @@ def render(mesh: OracleMesh, field: torch.Tensor, params: Dict[str, torch.Tensor
     if return_aux:
         out["aux"] = aux
     return out
+
+
+# =====================================================================================
+# training mode with autograd: the oracle of the fused training step
+# =====================================================================================
+class _GradientScaler(torch.autograd.Function):
+    """model.py:195-205"""
+
+    @staticmethod
+    def forward(ctx, colors, sigmas, ray_dist):
+        ctx.save_for_backward(ray_dist)
+        return colors, sigmas, ray_dist
+
+    @staticmethod
+    def backward(ctx, g_colors, g_sigmas, g_dist):
+        (ray_dist,) = ctx.saved_tensors
+        scaling = torch.square(ray_dist).clamp(0, 1)
+        return g_colors * scaling, g_sigmas * scaling, g_dist
+
+
+def interpolate_torch(vertex_indices, bary, field):
+    """interpolate_values (tetrahedra_tracer.cu:203-220) in differentiable torch: vertex_indices i64[...,4] (-1 = empty), bary f32[...,3],
+    field f32[C,V] -> [...,C]; the gradient w.r.t. the field is interpolate_values_backward (:231-247); none flows to the weights
+    (tetranerf/utils/extension/__init__.py:36-42 returns None for them)."""
+    vi = torch.as_tensor(vertex_indices).long()
+    w = torch.as_tensor(bary).detach()
+    ok = (vi >= 0).to(field.dtype)
+    F = field.t()  # [V,C]
+    safe = vi.clamp_min(0)
+    w0 = 1.0 - w.sum(-1)
+    out = (w[..., 0:1] * ok[..., 1:2]) * F[safe[..., 1]] + (w[..., 1:2] * ok[..., 2:3]) * F[safe[..., 2]] + (w[..., 2:3] * ok[..., 3:4]) * F[safe[..., 3]] \
+        + (w0[..., None] * ok[..., 0:1]) * F[safe[..., 0]]
+    return out
+
+
+def render_train(mesh: OracleMesh, field: torch.Tensor, params: Dict[str, torch.Tensor], origins, directions, cfg: RenderConfig,
+                 jitter_coarse=None, jitter_fine=None, use_gradient_scaling: bool = False, nthreads: int = 0):
+    """TetrahedraNerf.get_outputs in TRAINING mode (model.py:520-662) in differentiable torch-CPU fp32: `field` and the entries of `params`
+    may require grad.  jitter_coarse f32[R,S_c+1] / jitter_fine f32[R,S_f+1] are the uniform draws of the two stratified samplers, indexed by
+    RAY (the reference draws them with torch.rand on the non-empty rays).  Training-mode renderer: white background, no nan_to_num / clamp."""
+    o = torch.as_tensor(np.asarray(origins), dtype=torch.float32).reshape(-1, 3)
+    d = torch.as_tensor(np.asarray(directions), dtype=torch.float32).reshape(-1, 3)
+    R = o.shape[0]
+    assert cfg.num_fine_samples > 0
+    tr = mesh.trace_rays(o.numpy(), d.numpy(), cfg.max_intersected_triangles, nthreads=nthreads)
+    num_visited = torch.from_numpy(tr["num_visited_cells"])
+    hd = torch.from_numpy(tr["hit_distances"])
+    nears = hd[:, 0, 0][:, None]
+    fars = torch.gather(hd[:, :, 1], 1, (num_visited[:, None].long() - 1).clamp_min(0))
+    ray_mask = num_visited > 0
+    m = ray_mask.numpy()
+    nears_r, fars_r = nears[ray_mask], fars[ray_mask]
+    trm = {k: v[m] for k, v in tr.items()}
+    dirs_r = d[ray_mask]
+    jc = torch.as_tensor(jitter_coarse)[ray_mask] if jitter_coarse is not None else None
+    jf = torch.as_tensor(jitter_fine)[ray_mask] if jitter_fine is not None else None
+
+    def match(euclid_bins):
+        dist = ((euclid_bins[:, 1:] + euclid_bins[:, :-1]) / 2).contiguous()
+        return find_visited_cells(trm["num_visited_cells"], trm["visited_cells"], trm["barycentric_coordinates"], trm["hit_distances"],
+                                  trm["vertex_indices"], dist.detach().numpy(), nthreads=nthreads)
+
+    with torch.no_grad():  # the coarse pass only feeds the (detached) PDF bins
+        euclid, sbins = coarse_bins(cfg, nears_r, fars_r, num_visited[ray_mask], hd[ray_mask], jc)
+        tc = match(euclid)
+        fv = interpolate_torch(tc["vertex_indices"], tc["barycentric_coordinates"], field.detach())
+        density_coarse = density_head(params, mlp_base(params, fv))
+        weights = get_weights((euclid[:, 1:] - euclid[:, :-1])[..., None], density_coarse)
+        euclid, sbins = pdf_bins(cfg, sbins, weights, nears_r, fars_r, u_rand=jf)
+    tc = match(euclid)
+    fv = interpolate_torch(tc["vertex_indices"], tc["barycentric_coordinates"], field)
+    base = mlp_base(params, fv)
+    sigmas = density_head(params, base)
+    enc = nerf_encoding_dirs(dirs_r)[:, None, :].expand(-1, base.shape[1], -1)
+    colors = color_head(params, base, enc)
+    if use_gradient_scaling:
+        ray_dist = (sbins[:, 1:] + sbins[:, :-1])[..., None]  # spacing_ends + spacing_starts (model.py:629)
+        colors, sigmas, _ = _GradientScaler.apply(colors, sigmas, ray_dist)
+    deltas = (euclid[:, 1:] - euclid[:, :-1])[..., None]
+    weights = get_weights(deltas, sigmas)
+    comp = torch.sum(weights * colors, dim=-2)
+    accum = torch.sum(weights, dim=-2)
+    rgb_r = comp + 1.0 * (1.0 - accum)  # RGBRenderer in training: no nan_to_num, no clamp
+    steps = (euclid[:, 1:] + euclid[:, :-1]) / 2
+    cumw = torch.cumsum(weights[..., 0].detach(), dim=-1)
+    mi = torch.clamp(torch.searchsorted(cumw, torch.ones((weights.shape[0], 1)) * 0.5, side="left"), 0, steps.shape[-1] - 1)
+    depth_r = torch.gather(steps, dim=-1, index=mi)
+    idx = torch.nonzero(ray_mask).flatten()
+    rgb = torch.ones((R, 3), dtype=torch.float32).index_copy(0, idx, rgb_r)
+    acc = torch.zeros((R, 1), dtype=torch.float32).index_copy(0, idx, accum)
+    depth = torch.full((R, 1), cfg.far_plane, dtype=torch.float32).index_copy(0, idx, depth_r)
+    return {"rgb": rgb, "accumulation": acc, "depth": depth, "ray_mask": ray_mask,
+            "aux": {"fine_euclid": euclid.detach(), "sigmas": sigmas.detach(), "colors": colors.detach(), "weights": weights.detach(), "matched": tc}}

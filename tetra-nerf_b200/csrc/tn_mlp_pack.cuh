@@ -10,7 +10,10 @@
 
 namespace tn {
 
-static __global__ void k_pack_weights(const float *__restrict__ W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *__restrict__ img) {
+// kb_stride: bytes between consecutive 64-wide K blocks; lo_off: bytes from a hi block to its lo block.  The forward image uses
+// (32768, 16384): per K block [hi][lo]; the backward image (tn_mlp_bwd.cuh) uses (16384, 32768): [hi kb0][hi kb1][lo kb0][lo kb1].
+static __global__ void k_pack_weights(const float *__restrict__ W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *__restrict__ img,
+                                      uint32_t kb_stride, uint32_t lo_off) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 128u * K) return;
     const uint32_t n = idx / K, k = idx % K;
@@ -18,13 +21,14 @@ static __global__ void k_pack_weights(const float *__restrict__ W, uint32_t row_
     const __nv_bfloat16 hi = __float2bfloat16_rn(w);
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
     const uint32_t kb = k >> 6, kk = k & 63u;
-    const uint32_t off = kb * 32768u + tc::sw128_offset(n, kk);
+    const uint32_t off = kb * kb_stride + tc::sw128_offset(n, kk);
     *reinterpret_cast<__nv_bfloat16 *>(img + off) = hi;
-    *reinterpret_cast<__nv_bfloat16 *>(img + off + 16384u) = lo;
+    *reinterpret_cast<__nv_bfloat16 *>(img + off + lo_off) = lo;
 }
 
-static inline void launch_pack_weights(const float *W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *img, cudaStream_t s) {
-    k_pack_weights<<<(128u * K + 255u) / 256u, 256, 0, s>>>(W, row_stride, k0, K, img);
+static inline void launch_pack_weights(const float *W, uint32_t row_stride, uint32_t k0, uint32_t K, uint8_t *img, cudaStream_t s,
+                                       uint32_t kb_stride = 32768u, uint32_t lo_off = 16384u) {
+    k_pack_weights<<<(128u * K + 255u) / 256u, 256, 0, s>>>(W, row_stride, k0, K, img, kb_stride, lo_off);
 }
 
 }  // namespace tn

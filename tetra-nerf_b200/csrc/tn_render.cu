@@ -15,6 +15,7 @@
 
 #include "tn_common.cuh"
 #include "tn_mlp.cuh"
+#include "tn_mlp_bwd.cuh"
 #include "tn_mlp_pack.cuh"
 
 namespace tn {
@@ -43,6 +44,18 @@ struct RenderState {
     uint4 *vi_c = nullptr;
     float *ebins_f = nullptr, *bary_f = nullptr, *out_f = nullptr, *dirbias = nullptr;
     uint4 *vi_f = nullptr;
+    // training (tn_render_train_forward / _backward): backward weight image, per-sample head gradients, accumulators
+    uint8_t *wimg_bwd = nullptr;       // 7 stages of 32 KB (tn_mlp_bwd.cuh)
+    float *sbins_f = nullptr, *enc = nullptr;   // [R,S2+1] spacing bins of the fine pass, [R,27] encoded directions (per slot)
+    float4 *dout = nullptr;            // [R*S2] gradients at the head pre-activations
+    float *gshadow = nullptr, *gw = nullptr, *g_dirbias = nullptr;
+    uint8_t *scratch = nullptr;
+    size_t cap_train_R = 0, cap_train_S2 = 0, cap_scratch = 0;
+    uint32_t gshadow_V = 0;
+    // what the last training forward ran with (the backward continues from its buffers)
+    bool train_valid = false;
+    uint32_t t_R = 0, t_M = 0, t_Sc = 0, t_Sf = 0, t_S2 = 0;
+    float t_bg[3] = {1.f, 1.f, 1.f};
     // fused pixel gather (tn_render_set_gather): peer[k] = rank k's [world * rays_per_rank, 6] gathered-pixel buffer
     float *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t gather_world = 0, gather_rank = 0, gather_stride = 0;
@@ -66,6 +79,8 @@ void free_render(tn_tracer *h) {
     RenderState *r = h->render;
     free_ws(r);
     cudaFree(r->fshadow); cudaFree(r->wimg); cudaFree(r->bias); cudaFree(r->head); cudaFree(r->w4dir);
+    cudaFree(r->wimg_bwd); cudaFree(r->sbins_f); cudaFree(r->enc); cudaFree(r->dout); cudaFree(r->gshadow); cudaFree(r->gw); cudaFree(r->g_dirbias);
+    cudaFree(r->scratch);
     for (auto &e : r->ev) if (e) cudaEventDestroy(e);
     delete r;
     h->render = nullptr;
@@ -129,6 +144,10 @@ struct SampleParams {
     float *rgb, *acc, *depth;
     uint8_t *mask;
     float far_plane, bg0, bg1, bg2;
+    // training mode (model.py:169-174 stratified bins, PDFSampler train_stratified, RGBRenderer without nan_to_num / clamp)
+    uint32_t train;
+    const float *jit_c, *jit_f;   // [R,Sc+1], [R,Sf+1] uniform [0,1) draws indexed by RAY (nullptr: the eval-mode bins)
+    float *sbins_f, *enc;         // saved for the backward: spacing bins of the fine pass [slot,S2+1], encoded direction [slot,27]
     // fused pixel gather: when gather_world > 0 every rendered pixel is also stored, as (r, g, b, accumulation, depth, mask), at row
     // gather_rank * gather_stride + ray of EVERY rank's gathered buffer (peer[k] is mapped peer memory: stores travel over NVLink)
     float *peer[8];
@@ -260,7 +279,12 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const Sampl
         smem_scan_add(cum, n + 1, lane);
     }
     for (uint32_t j = lane; j <= S; j += 32) {
-        const float b = linspace_f(0.f, 1.f, S + 1, j);
+        float b = linspace_f(0.f, 1.f, S + 1, j);
+        if (p.jit_c != nullptr) {  // stratified training bins (model.py:169-174; nerfstudio SpacedSampler): jitter between the neighbouring bin centres
+            const float lower = j == 0 ? b : (b + linspace_f(0.f, 1.f, S + 1, j - 1)) / 2.0f;
+            const float upper = j == S ? b : (linspace_f(0.f, 1.f, S + 1, j + 1) + b) / 2.0f;
+            b = lower + (upper - lower) * __ldg(p.jit_c + (size_t)ray * (S + 1) + j);
+        }
         float eu = b * far + (1.f - b) * near;  // spacing_to_euclidean_fn (model.py:177)
         float sb = b;
         if (p.biased) {
@@ -324,6 +348,10 @@ __device__ __forceinline__ void dir_bias(const SampleParams &p, uint32_t ray, ui
             enc[24 + a] = dd[a];
         }
     }
+    if (p.train) {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) if (lane == k) p.enc[(size_t)slot * 27 + k] = enc[k];
+    }
     for (uint32_t o = lane; o < 128; o += 32) {
         float acc = p.w4dir[128 * 27 + o];
 #pragma unroll
@@ -369,7 +397,7 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_fine(const SampleP
     // new bins -> x[0..nb)
     const float u_end = (float)(1.0 - 1.0 / (double)nb), u_off = (float)(1.0 / (2.0 * (double)nb));
     for (uint32_t i = lane; i < nb; i += 32) {
-        const float u = linspace_f(0.f, u_end, nb, i) + u_off;
+        const float u = linspace_f(0.f, u_end, nb, i) + (p.jit_f != nullptr ? __ldg(p.jit_f + (size_t)ray * nb + i) / (float)nb : u_off);  // train_stratified
         uint32_t lo = 0, hi = S + 1;  // searchsorted(cdf, u, side="right"): first idx with cdf[idx] > u
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
         const uint32_t below = (uint32_t)min(max((int)lo - 1, 0), (int)S), above = min(lo, S);
@@ -400,6 +428,7 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_fine(const SampleP
         const float eu = b * far + (1.f - b) * near;
         y[j] = eu;
         p.ebins_f[(size_t)slot * (S2 + 1) + j] = eu;
+        if (p.train) p.sbins_f[(size_t)slot * (S2 + 1) + j] = b;
     }
     __syncwarp();
     for (uint32_t j = lane; j < S2; j += 32) {
@@ -430,7 +459,8 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_composite(const SamplePar
     for (uint32_t j = lane; j < S2; j += 32) {
         const float4 c = of[j];
         const float wj = w[j];
-        r += wj * nan_to_num_f(c.y); g += wj * nan_to_num_f(c.z); b += wj * nan_to_num_f(c.w); a += wj;
+        if (p.train) { r += wj * c.y; g += wj * c.z; b += wj * c.w; a += wj; }  // RGBRenderer in training: no nan_to_num, no clamp
+        else { r += wj * nan_to_num_f(c.y); g += wj * nan_to_num_f(c.z); b += wj * nan_to_num_f(c.w); a += wj; }
     }
     r = warp_sum_f(r); g = warp_sum_f(g); b = warp_sum_f(b); a = warp_sum_f(a);
     // DepthRenderer("median"): first sample whose cumulative weight reaches 0.5
@@ -442,9 +472,119 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_composite(const SamplePar
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
     const uint32_t mi = min(first, S2 - 1);
-    // RGBRenderer (eval): comp + background * (1 - acc), clamped to [0,1]
-    store_pixel(p, ray, lane, fminf(fmaxf(r + p.bg0 * (1.f - a), 0.f), 1.f), fminf(fmaxf(g + p.bg1 * (1.f - a), 0.f), 1.f),
-                fminf(fmaxf(b + p.bg2 * (1.f - a), 0.f), 1.f), a, (eb[mi] + eb[mi + 1]) / 2.f, 1);
+    // RGBRenderer: comp + background * (1 - acc); clamped to [0,1] in eval mode only
+    float pr = r + p.bg0 * (1.f - a), pg = g + p.bg1 * (1.f - a), pb = b + p.bg2 * (1.f - a);
+    if (!p.train) { pr = fminf(fmaxf(pr, 0.f), 1.f); pg = fminf(fmaxf(pg, 0.f), 1.f); pb = fminf(fmaxf(pb, 0.f), 1.f); }
+    store_pixel(p, ray, lane, pr, pg, pb, a, (eb[mi] + eb[mi + 1]) / 2.f, 1);
+}
+
+// ---- backward of the compositing + field heads of the fine pass (model.py:621-637; RaySamples.get_weights, RGBRenderer and
+// AccumulationRenderer of nerfstudio, GradientScaler model.py:195-205): one warp per active ray.
+//   w_j = (1 - exp(-x_j)) T_j,  x_j = delta_j sigma_j,  T_j = exp(-sum_{i<j} x_i);   rgb = sum w_j c_j + bg (1 - sum w_j),  acc = sum w_j
+//   dL/dw_j = g_j = grad_rgb . (c_j - bg) + grad_acc;   dL/dx_j = g_j (T_j - w_j) - sum_{k>j} g_k w_k;   dL/dc_j = grad_rgb w_j
+// then through Softplus / Sigmoid to the head PRE-activations, which is where the MLP backward kernel starts.
+struct CompositeBwdParams {
+    uint32_t S2, use_gradient_scaling;
+    const uint32_t *n_active, *ray_list;
+    const float *ebins_f, *sbins_f, *out_f;
+    const float *grad_rgb, *grad_acc;  // [R,3], [R] or nullptr
+    float bg0, bg1, bg2;
+    float4 *dout;                      // [slot * S2 + j]
+    float *sums;                       // 4 floats: sum d sigma_pre, sum d z_r, d z_g, d z_b (bias gradients of the two heads)
+};
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_composite_bwd(const CompositeBwdParams p) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * SAMPLE_WARPS + warp;
+    if (slot >= *p.n_active) return;
+    const uint32_t S2 = p.S2;
+    float *w = sm + (size_t)warp * (4 * ((size_t)S2 + 2)), *tr = w + S2 + 2, *gw = tr + S2 + 2, *fx = gw + S2 + 2;
+    const uint32_t ray = p.ray_list[slot];
+    const float *eb = p.ebins_f + (size_t)slot * (S2 + 1);
+    const float4 *of = reinterpret_cast<const float4 *>(p.out_f) + (size_t)slot * S2;
+    const float gr = p.grad_rgb[3 * (size_t)ray], gg = p.grad_rgb[3 * (size_t)ray + 1], gb = p.grad_rgb[3 * (size_t)ray + 2];
+    const float ga = p.grad_acc != nullptr ? p.grad_acc[ray] : 0.f;
+    for (uint32_t j = lane; j < S2; j += 32) tr[j] = (eb[j + 1] - eb[j]) * of[j].x;  // x_j
+    __syncwarp();
+    smem_scan_add(tr, S2, lane);  // inclusive cumsum of x
+    for (uint32_t j = lane; j < S2; j += 32) {
+        const float excl = j == 0 ? 0.f : tr[j - 1];
+        const float x = (eb[j + 1] - eb[j]) * of[j].x;
+        const float T = expf(-excl);
+        float wj = (1.f - expf(-x)) * T;
+        const bool fin = isfinite(wj);  // nan_to_num in the forward: a replaced weight carries no gradient
+        wj = fin ? wj : nan_to_num_f(wj);
+        const float4 c = of[j];
+        const float g = fin ? (gr * (c.y - p.bg0) + gg * (c.z - p.bg1) + gb * (c.w - p.bg2) + ga) : 0.f;
+        w[j] = wj;
+        gw[j] = g * wj;
+        fx[j] = fin ? g * (T - wj) : 0.f;  // first term of dL/dx_j
+    }
+    __syncwarp();
+    const float total = smem_scan_add(gw, S2, lane);  // inclusive cumsum of g_k w_k -> suffix_j = total - gw[j]
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (uint32_t j = lane; j < S2; j += 32) {
+        const float4 c = of[j];
+        const float delta = eb[j + 1] - eb[j];
+        float dsig = delta * (fx[j] - (total - gw[j]));
+        float dr = gr * w[j], dg = gg * w[j], db = gb * w[j];
+        if (p.use_gradient_scaling) {  // model.py:195-205,625-630: squared (spacing_start + spacing_end), clamped to [0,1]
+            const float *sb = p.sbins_f + (size_t)slot * (S2 + 1);
+            const float rd = sb[j] + sb[j + 1];
+            const float sc = fminf(fmaxf(rd * rd, 0.f), 1.f);
+            dsig *= sc; dr *= sc; dg *= sc; db *= sc;
+        }
+        const float4 o = make_float4(dsig * (-expm1f(-c.x)),      // Softplus'(s) = 1 - exp(-softplus(s))
+                                     dr * c.y * (1.f - c.y), dg * c.z * (1.f - c.z), db * c.w * (1.f - c.w));  // Sigmoid' = c (1 - c)
+        p.dout[(size_t)slot * S2 + j] = o;
+        s0 += o.x; s1 += o.y; s2 += o.z; s3 += o.w;
+    }
+    s0 = warp_sum_f(s0); s1 = warp_sum_f(s1); s2 = warp_sum_f(s2); s3 = warp_sum_f(s3);
+    if (lane == 0) { atomicAdd(p.sums, s0); atomicAdd(p.sums + 1, s1); atomicAdd(p.sums + 2, s2); atomicAdd(p.sums + 3, s3); }
+}
+
+// ---- after k_mlp_bwd: the direction part of mlp_head.layers.0 (W4[:, :27], b4) from the per-ray bias gradients, then all twelve
+// parameter gradients in torch layout.  One block per hidden unit k; lane j < 27 owns W4[k, j], lane 27 the bias.
+__global__ void __launch_bounds__(32) k_dirbias_grads(const uint32_t *__restrict__ n_active, const float *__restrict__ g_dirbias, const float *__restrict__ enc,
+                                                       float *__restrict__ gw) {
+    const uint32_t k = blockIdx.x, lane = threadIdx.x, n = *n_active;
+    float acc = 0.f;
+    for (uint32_t s = 0; s < n; ++s) {
+        const float g = __ldg(g_dirbias + (size_t)s * 128 + k);
+        if (lane < 27) acc = fmaf(g, __ldg(enc + (size_t)s * 27 + lane), acc);
+        else if (lane == 27) acc += g;
+    }
+    if (lane < 27) gw[GW_W4DIR + k * 27 + lane] = acc;
+    else if (lane == 27) gw[GW_B4 + k] = acc;
+}
+struct GradOut { float *p[12]; };
+__global__ void k_scatter_grads(const float *__restrict__ gw, const GradOut o) {
+    // o.p: mlp_base.layers.{0,1,2}.{weight,bias}, mlp_head.layers.0.{weight,bias}, field_output_color.net.{weight,bias}, field_output_density.net.{weight,bias}
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 8192) o.p[0][i] = gw[GW_W1 + i];
+    if (i < 16384) { o.p[2][i] = gw[GW_W2 + i]; o.p[4][i] = gw[GW_W3 + i]; }
+    if (i < 128 * 155) {
+        const uint32_t k = i / 155, j = i % 155;
+        o.p[6][i] = j < 27 ? gw[GW_W4DIR + k * 27 + j] : gw[GW_W4B + k * 128 + (j - 27)];
+    }
+    if (i < 128) { o.p[1][i] = gw[GW_B1 + i]; o.p[3][i] = gw[GW_B2 + i]; o.p[5][i] = gw[GW_B3 + i]; o.p[7][i] = gw[GW_B4 + i]; o.p[10][i] = gw[GW_WD + i]; }
+    if (i < 384) o.p[8][i] = gw[GW_WC + i];
+    if (i < 3) o.p[9][i] = gw[GW_SUMS + 1 + i];
+    if (i == 0) o.p[11][0] = gw[GW_SUMS];
+}
+__global__ void k_transpose_v64(const float *__restrict__ in, float *__restrict__ out, uint32_t V) {  // [V,64] -> [64,V]
+    __shared__ float tile[32][65];
+    const uint32_t v0 = blockIdx.x * 32;
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t v = v0 + r;
+        tile[r][threadIdx.x] = v < V ? in[(size_t)v * 64 + threadIdx.x] : 0.f;
+        tile[r][threadIdx.x + 32] = v < V ? in[(size_t)v * 64 + 32 + threadIdx.x] : 0.f;
+    }
+    __syncthreads();
+    for (uint32_t c = threadIdx.y; c < 64; c += blockDim.y) {
+        const uint32_t v = v0 + threadIdx.x;
+        if (v < V) out[(size_t)c * V + v] = tile[threadIdx.x][c];
+    }
 }
 
 // single-pass configuration (num_fine_samples == 0, model.py:573 skipped): colours come from the first and only pass -- the
@@ -502,14 +642,26 @@ extern "C" int tn_render_set_weights(tn_tracer *h, const float *const *P, void *
     launch_pack_weights(P[4], 128, 0, 128, r->wimg + 32768 + 65536, s);   // mlp_base.layers.2.weight
     launch_pack_weights(P[6], 155, 27, 128, r->wimg + 32768 + 131072, s); // mlp_head.layers.0.weight [128,155], base part
     k_pack_small<<<1, 128, 0, s>>>(P[1], P[3], P[5], P[6], P[7], P[8], P[9], P[10], P[11], r->bias, r->head, r->w4dir);
-    h->launches += 5;
+    // backward image (tn_mlp_bwd.cuh): stage 0 = [W1 hi | W1 lo]; then per 128-wide layer [hi kb0 | hi kb1][lo kb0 | lo kb1]
+    if (!r->wimg_bwd) TN_CUDA(cudaMalloc((void **)&r->wimg_bwd, BWD_WIMG_BYTES));
+    launch_pack_weights(P[0], 64, 0, 64, r->wimg_bwd, s, 16384u, 16384u);
+    launch_pack_weights(P[2], 128, 0, 128, r->wimg_bwd + 1 * BWD_STAGE, s, 16384u, 32768u);
+    launch_pack_weights(P[4], 128, 0, 128, r->wimg_bwd + 3 * BWD_STAGE, s, 16384u, 32768u);
+    launch_pack_weights(P[6], 155, 27, 128, r->wimg_bwd + 5 * BWD_STAGE, s, 16384u, 32768u);
+    h->launches += 9;
     TN_CUDA(cudaGetLastError());
     r->have_weights = true;
     return TN_OK;
 }
 
-extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
-                         float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, void *stream) {
+// training-mode inputs of the forward (nullptr = eval)
+struct TrainFwd {
+    const float *jit_c, *jit_f;
+};
+static int ensure_train_ws(RenderState *r, size_t R, size_t S2, uint32_t V, int sms);
+
+static int render_impl(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
+                       float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, const TrainFwd *tf, void *stream) {
     if (!h || !cfg) return fail(TN_ERR_ARG, "null argument");
     RenderState *r = h->render;
     if (!r || !r->fshadow || !r->have_weights) return fail(TN_ERR_STATE, "tn_render: call tn_render_set_field and tn_render_set_weights first");
@@ -517,6 +669,7 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     if (r->V != h->mesh.V) return fail(TN_ERR_ARG, "tn_render: field has a different vertex count than the mesh");
     const uint32_t M = cfg->max_ray_triangles, Sc = cfg->num_samples, Sf = cfg->num_fine_samples;
     if (Sc == 0 || Sc > 4096 || Sf > 4096) return fail(TN_ERR_ARG, "tn_render: num_samples must be in [1,4096]");
+    if (tf != nullptr && Sf == 0) return fail(TN_ERR_ARG, "tn_render_train_forward: the fused training step needs num_fine_samples > 0");
     if (R == 0) return TN_OK;
     const bool single = Sf == 0;                       // one pass only: the colours come from the coarse samples
     const uint32_t S2 = single ? Sc : Sc + Sf + 1;     // PDFSampler include_original (model.py:463)
@@ -524,6 +677,13 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     cudaStream_t s = (cudaStream_t)stream;
     int rc = ensure_ws(r, R, M, Sc, S2);
     if (rc) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (tf != nullptr) {
+        rc = ensure_train_ws(r, R, S2, r->V, sms);
+        if (rc) return rc;
+    }
+    r->train_valid = false;
     TN_CUDA(cudaMemsetAsync(r->n_active, 0, 16, s));
 #define TN_EV(i) do { if (r->profile) cudaEventRecord(r->ev[i], s); } while (0)
     TN_EV(0);  // the "trace" interval includes the L2 warm-up it exists for
@@ -544,6 +704,7 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     p.ebins_f = r->ebins_f; p.bary_f = r->bary_f; p.vi_f = r->vi_f; p.dirbias = r->dirbias; p.w4dir = r->w4dir; p.out_f = r->out_f;
     p.rgb = d_rgb; p.acc = d_acc; p.depth = d_depth; p.mask = d_mask;
     p.far_plane = cfg->far_plane; p.bg0 = cfg->background[0]; p.bg1 = cfg->background[1]; p.bg2 = cfg->background[2];
+    if (tf != nullptr) { p.train = 1; p.jit_c = tf->jit_c; p.jit_f = tf->jit_f; p.sbins_f = r->sbins_f; p.enc = r->enc; }
     if (r->gather_world) {
         if (R > r->gather_stride) return fail(TN_ERR_ARG, "tn_render: more rays than the gathered-pixel buffers were sized for (tn_render_set_gather)");
         for (int k = 0; k < 8; ++k) p.peer[k] = r->peer[k];
@@ -558,8 +719,6 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     TN_CUDA(cudaFuncSetAttribute(k_composite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     TN_CUDA(cudaFuncSetAttribute(k_mlp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
     TN_CUDA(cudaFuncSetAttribute(k_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const uint32_t gridR = (R + SAMPLE_WARPS - 1) / SAMPLE_WARPS;
 
     k_sample_coarse<<<gridR, SAMPLE_WARPS * 32, smem_sc, s>>>(p);
@@ -585,6 +744,97 @@ extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float 
     k_composite<<<gridR, SAMPLE_WARPS * 32, smem_c, s>>>(p);
     TN_EV(6);
 #undef TN_EV
+    h->launches += 5;
+    TN_CUDA(cudaGetLastError());
+    if (tf != nullptr) {
+        r->train_valid = true;
+        r->t_R = R; r->t_M = M; r->t_Sc = Sc; r->t_Sf = Sf; r->t_S2 = S2;
+        r->t_bg[0] = cfg->background[0]; r->t_bg[1] = cfg->background[1]; r->t_bg[2] = cfg->background[2];
+    }
+    return TN_OK;
+}
+
+static int ensure_train_ws(RenderState *r, size_t R, size_t S2, uint32_t V, int sms) {
+    if (R > r->cap_train_R || S2 > r->cap_train_S2) {
+        cudaFree(r->sbins_f); cudaFree(r->enc); cudaFree(r->dout); cudaFree(r->g_dirbias);
+        r->sbins_f = r->enc = r->g_dirbias = nullptr; r->dout = nullptr;
+        R = std::max(R, r->cap_train_R); S2 = std::max(S2, r->cap_train_S2);
+        TN_CUDA(cudaMalloc((void **)&r->sbins_f, 4 * R * (S2 + 1)));
+        TN_CUDA(cudaMalloc((void **)&r->enc, 4 * R * 27));
+        TN_CUDA(cudaMalloc((void **)&r->dout, 16 * R * S2));
+        TN_CUDA(cudaMalloc((void **)&r->g_dirbias, 512 * R));
+        r->cap_train_R = R; r->cap_train_S2 = S2;
+    }
+    if (!r->gw) TN_CUDA(cudaMalloc((void **)&r->gw, sizeof(float) * GW_TOTAL));
+    if (r->gshadow_V != V) {
+        cudaFree(r->gshadow); r->gshadow = nullptr;
+        TN_CUDA(cudaMalloc((void **)&r->gshadow, sizeof(float) * 64 * (size_t)V));
+        r->gshadow_V = V;
+    }
+    const size_t need = (size_t)sms * BWD_SCRATCH_PER_CTA;
+    if (r->cap_scratch < need) {
+        cudaFree(r->scratch); r->scratch = nullptr;
+        TN_CUDA(cudaMalloc((void **)&r->scratch, need));
+        r->cap_scratch = need;
+    }
+    return TN_OK;
+}
+
+extern "C" int tn_render(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
+                         float *d_rgb, float *d_acc, float *d_depth, uint8_t *d_mask, void *stream) {
+    return render_impl(h, cfg, d_origins, d_directions, R, d_rgb, d_acc, d_depth, d_mask, nullptr, stream);
+}
+
+// ---- fused training step (model.py:520-662 in training mode + autograd) ------------------------------------------------
+// forward: the fused pipeline with stratified bins (d_jitter_coarse f32[R,Sc+1], d_jitter_fine f32[R,Sf+1], uniform [0,1), indexed by
+// ray; nullptr = eval bins) and the training-mode RGB renderer (no nan_to_num, no clamp).  Keeps what the backward needs.
+extern "C" int tn_render_train_forward(tn_tracer *h, const tn_render_config *cfg, const float *d_origins, const float *d_directions, uint32_t R,
+                                       const float *d_jitter_coarse, const float *d_jitter_fine, float *d_rgb, float *d_acc, float *d_depth,
+                                       uint8_t *d_mask, void *stream) {
+    TrainFwd tf{d_jitter_coarse, d_jitter_fine};
+    return render_impl(h, cfg, d_origins, d_directions, R, d_rgb, d_acc, d_depth, d_mask, &tf, stream);
+}
+
+// backward of the LAST tn_render_train_forward: d_grad_rgb f32[R,3] (dL/d rgb), d_grad_acc f32[R] or NULL (dL/d accumulation) ->
+// d_grad_field f32[64,V] and the twelve MLP parameter gradients (same order / layouts as tn_render_set_weights); every output element
+// is written.  The coarse pass carries no gradient (PDFSampler detaches its bins).  No [samples,128] tensor touches HBM.
+extern "C" int tn_render_train_backward(tn_tracer *h, const float *d_grad_rgb, const float *d_grad_acc, int use_gradient_scaling,
+                                        float *d_grad_field, float *const *d_grad_params12, void *stream) {
+    if (!h || !d_grad_rgb || !d_grad_field || !d_grad_params12) return fail(TN_ERR_ARG, "null argument");
+    RenderState *r = h->render;
+    if (!r || !r->train_valid) return fail(TN_ERR_STATE, "tn_render_train_backward: no training forward to continue from");
+    DeviceGuard g(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const uint32_t R = r->t_R, S2 = r->t_S2, V = r->V;
+    TN_CUDA(cudaMemsetAsync(r->gw, 0, sizeof(float) * GW_TOTAL, s));
+    TN_CUDA(cudaMemsetAsync(r->gshadow, 0, sizeof(float) * 64 * (size_t)V, s));
+    TN_CUDA(cudaMemsetAsync(r->g_dirbias, 0, 512 * (size_t)R, s));
+    TN_CUDA(cudaMemsetAsync(r->n_active + 3, 0, 4, s));  // tile counter of the backward kernel (word 3 of the 16-byte block)
+    CompositeBwdParams cb{};
+    cb.S2 = S2; cb.use_gradient_scaling = use_gradient_scaling ? 1u : 0u; cb.n_active = r->n_active; cb.ray_list = r->ray_list;
+    cb.ebins_f = r->ebins_f; cb.sbins_f = r->sbins_f; cb.out_f = r->out_f; cb.grad_rgb = d_grad_rgb; cb.grad_acc = d_grad_acc;
+    cb.bg0 = r->t_bg[0]; cb.bg1 = r->t_bg[1]; cb.bg2 = r->t_bg[2]; cb.dout = r->dout; cb.sums = r->gw + GW_SUMS;
+    const size_t smem_cb = SAMPLE_WARPS * sizeof(float) * 4 * ((size_t)S2 + 2);
+    TN_CUDA(cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
+    const uint32_t gridR = (R + SAMPLE_WARPS - 1) / SAMPLE_WARPS;
+    k_composite_bwd<<<gridR, SAMPLE_WARPS * 32, smem_cb, s>>>(cb);
+    MlpBwdParams bp{};
+    bp.n_active = r->n_active; bp.S = S2; bp.vi = r->vi_f; bp.bary = r->bary_f; bp.fshadow = r->fshadow; bp.wimg = r->wimg_bwd;
+    bp.bias = r->bias; bp.head = r->head; bp.dirbias = r->dirbias; bp.dout = r->dout; bp.scratch = r->scratch; bp.gshadow = r->gshadow;
+    bp.gw = r->gw; bp.g_dirbias = r->g_dirbias; bp.tile_ctr = r->n_active + 3;
+    TN_CUDA(cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
+    const uint32_t tiles = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
+    k_mlp_bwd<<<std::min<uint32_t>(tiles, (uint32_t)sms), BWD_THREADS, BWD_SMEM_BYTES, s>>>(bp);
+    k_dirbias_grads<<<128, 32, 0, s>>>(r->n_active, r->g_dirbias, r->enc, r->gw);
+    GradOut go{};
+    for (int i = 0; i < 12; ++i) {
+        if (!d_grad_params12[i]) return fail(TN_ERR_ARG, "tn_render_train_backward: null parameter gradient pointer");
+        go.p[i] = d_grad_params12[i];
+    }
+    k_scatter_grads<<<(128 * 155 + 255) / 256, 256, 0, s>>>(r->gw, go);
+    k_transpose_v64<<<(V + 31) / 32, dim3(32, 8), 0, s>>>(r->gshadow, d_grad_field, V);
     h->launches += 5;
     TN_CUDA(cudaGetLastError());
     return TN_OK;

@@ -178,7 +178,12 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams p) {
         p.keys[row + nfaces] = ((u64)__float_as_uint(t_out) << 32) | fout;
         nfaces++;
         const uint32_t next = sel4u(jout, nb.x, nb.y, nb.z, nb.w);
-        if (next == TN_EMPTY || nfaces >= p.M - 1) break;  // left the mesh, or the M-1 nearest faces are in (optix_trace_rays.cu:312-315)
+        if (next == TN_EMPTY) break;  // left the mesh
+        // Hit cap (optix_trace_rays.cu:312-315; pinned: the M-1 smallest (t, face id) keys survive).  The first M-1 faces in WALK order
+        // are those only if nothing behind them ties with or precedes the last one (a zero-length tetrahedron at the cut sorts its
+        // exit face first when that face has the smaller id) -- the walk cannot know without going on, so a ray that really is
+        // truncated goes to the exact all-hits stage and its rank selection.  M = 512 never truncates on the meshes of SURVEY §8d.
+        if (nfaces >= p.M - 1) { exact = true; break; }
         c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out;
     }
     if (exact) {
@@ -340,7 +345,8 @@ __global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
         }
         if (lane == 0) p.keys[row + nfaces] = ((u64)__float_as_uint(t_out) << 32) | fout;
         nfaces++;
-        if (next == TN_EMPTY || nfaces >= p.M - 1) break;  // left the mesh, or the M-1 nearest faces are in (optix_trace_rays.cu:312-315)
+        if (next == TN_EMPTY) break;                       // left the mesh
+        if (nfaces >= p.M - 1) { exact = true; break; }    // truncated by the hit cap: exact stage (see k_walk)
         c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out;
     }
     if (lane != 0) return;

@@ -19,6 +19,7 @@ installed; otherwise the minimal look-alikes of `_ns_compat` are used.
 from __future__ import annotations
 
 import dataclasses
+import os
 from dataclasses import dataclass
 from pathlib import Path
 from typing import Any, Dict, List, Literal, Optional
@@ -294,7 +295,27 @@ class TetrahedraNerf(Model):
             st = RenderSettings(self.config.max_intersected_triangles, self.config.num_samples, self.config.num_fine_samples,
                                 self.config.use_biased_sampler, float(self.collider.far_plane), bg)
             return self._fused_renderer().render(origins, directions, st)
+        if self.training and torch.is_grad_enabled() and self._fused_supported() and self.config.num_fine_samples > 0 \
+                and os.environ.get("TETRANERF_B200_UNFUSED_TRAIN", "0") != "1":
+            return self._get_outputs_fused_train(origins, directions)
         return self._get_outputs_unfused(ray_bundle, origins, directions)
+
+    def _get_outputs_fused_train(self, origins, directions):
+        """training step on the fused CUDA pipeline: ONE differentiable op (forward + tcgen05 backward) instead of the reference's op
+        sequence; the stratified draws are the same two torch.rand calls the reference makes (model.py:169-174, PDFSampler)."""
+        from ..b200.render import PARAM_ORDER, FusedTrainRender, RenderSettings
+
+        c = self.config
+        bg = (1.0, 1.0, 1.0) if c.background_color == "white" else (0.0, 0.0, 0.0)
+        st = RenderSettings(c.max_intersected_triangles, c.num_samples, c.num_fine_samples, c.use_biased_sampler, float(self.collider.far_plane), bg)
+        fr = self._fused_renderer()
+        R, dev = origins.shape[0], origins.device
+        jc = torch.rand((R, c.num_samples + 1), dtype=torch.float32, device=dev) if getattr(self.sampler_uniform, "train_stratified", True) else None
+        jf = torch.rand((R, c.num_fine_samples + 1), dtype=torch.float32, device=dev) if getattr(self.sampler_pdf, "train_stratified", True) else None
+        named = dict(self.named_parameters())
+        rgb, acc, depth, mask = FusedTrainRender.apply(fr, st, c.use_gradient_scaling, origins, directions, jc, jf, self.tetrahedra_field,
+                                                       *[named[n] for n in PARAM_ORDER])
+        return {"rgb": rgb, "accumulation": acc, "depth": depth, "ray_mask": mask}
 
     def _field_at(self, tracer, traced, ray_mask, distances):
         matched = tracer.find_visited_cells(traced["num_visited_cells"][ray_mask], traced["visited_cells"][ray_mask],
