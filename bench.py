@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--workload", default="tetra-nerf", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="eval", choices=["eval", "train"])
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer-store gather (default) or NCCL all_gather")
+    ap.add_argument("--points", type=int, default=None, help="--mode train: points of the Delaunay mesh (default 300000 -> ~2.0 M tetrahedra)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -429,8 +430,122 @@ def main():
         dist.destroy_process_group()
 
 
+NUM_POINTS_TRAIN = 300_000  # BASELINE configs[2]: "dense 300k-point mesh" -> ~2.0 M tetrahedra
+
+
 def run_train(args, rank, world, dev, V, C, field, params, dist):
-    raise SystemExit("--mode train: see tetranerf.b200.train (fused training step)")
+    """BASELINE configs[2]: 300k-point mesh (~2.0 M tetrahedra), 8192 rays per batch, biased sampler, ONE training step = forward
+    (stratified bins) + loss + backward + DDP-style gradient averaging (N > 1) + optimizer step (RAdam lr 1e-3, registration.py:37-41)
+    through the plug-in API (TetrahedraNerf.forward / get_loss_dict).  `value` = rays/s with the ray batch and the target pixels
+    resident in HBM, `e2e` = with pinned-host rays + targets copied in and the loss read back every step.  The same steps on the
+    reference's op sequence (unfused CUDA ops + torch fp32 MLP + autograd, TETRANERF_B200_UNFUSED_TRAIN=1) are timed beside it."""
+    from tetranerf.b200.distributed import average_gradients
+    from tetranerf.nerfstudio import model as tnm
+
+    syn = synthetic()
+    R = args.rays
+    w = WORKLOADS[args.workload]
+    V, C = syn.delaunay_mesh(args.points or NUM_POINTS_TRAIN, seed=0)
+    field = syn.random_field(len(V), 64, seed=3, kind="normal")
+
+    def make_model():
+        cfg = tnm.TetrahedraNerfConfig(num_tetrahedra_vertices=len(V), num_tetrahedra_cells=len(C), num_samples=w["num_samples"],
+                                       num_fine_samples=w["num_fine_samples"], use_biased_sampler=w["use_biased_sampler"])
+        m = tnm.TetrahedraNerf(cfg)
+        sd = {"tetrahedra_vertices": torch.from_numpy(V), "tetrahedra_cells": torch.from_numpy(C), "tetrahedra_field": torch.from_numpy(field)}
+        sd.update(params)
+        m.load_state_dict(sd, strict=False)
+        return m.to(dev).train()
+
+    nsteps = args.warmup + args.steps
+    host = []
+    for i in range(nsteps):
+        o, d = syn.camera_rays(R, seed=5000 * (rank + 1) + i)
+        tgt = np.random.default_rng(9000 * (rank + 1) + i).random((R, 3), dtype=np.float32)
+        host.append(torch.from_numpy(np.concatenate([o, d, tgt], 1)).pin_memory())  # [R, 9]
+    devb = [t.to(dev) for t in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    host_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def run(mode_env: str, steps: int, warmup: int, e2e: bool):
+        os.environ["TETRANERF_B200_UNFUSED_TRAIN"] = mode_env
+        model = make_model()
+        opt = torch.optim.RAdam(model.parameters(), lr=1e-3)
+        tracer = model.get_tetrahedra_tracer()
+
+        def step(i):
+            b = host[i].to(dev, non_blocking=True) if e2e else devb[i]
+            out = model(tnm.RayBundle(origins=b[:, 0:3].contiguous(), directions=b[:, 3:6].contiguous()))
+            loss = model.get_loss_dict(out, {"image": b[:, 6:9]})["rgb_loss"]
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if world > 1:
+                average_gradients(model.parameters())
+            opt.step()
+            if e2e:
+                host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = tracer.launch_count()
+        for k in range(steps):
+            flush.fill_(k & 0xFF)
+            ev[k][0].record()
+            step(warmup + k)
+            ev[k][1].record()
+        torch.cuda.synchronize(dev)
+        launches = tracer.launch_count() - l0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        del model, opt
+        return float(t.item()), launches
+
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ms_total, launches = run("0", args.steps, args.warmup, False)
+    ms_e2e, _ = run("0", args.steps, args.warmup, True)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    usteps = max(3, args.steps // 4)
+    ms_unfused, _ = run("1", usteps, 3, False)
+    if rank == 0:
+        pk = peaks()
+        total = world * R * args.steps
+        S2 = w["num_samples"] + w["num_fine_samples"] + 1
+        # SURVEY §8d: forward 42.03 MFLOP/ray + backward 2 x the fine pass (the coarse pass is detached)
+        flop_step = R * (w["num_samples"] * FLOP_COARSE + 3 * S2 * FLOP_FINE)
+        ach = world * flop_step / (ms_total / args.steps * 1e-3) / 1e12
+        line = {
+            "metric": "rays/sec (train step fwd+bwd+optimizer, 8192-ray batch, ~2M-tet mesh)", "value": total / (ms_total * 1e-3), "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (trace/interp/compositing/optimizer) + bf16x3 tensor-core MLP fwd+bwd with f32 accumulate",
+            "data": "synthetic", "config": workload_config(args.workload, "train", R, world, len(C)) | {"points": int(len(V))},
+            "timing": {"l2": "flushed between timed steps (256 MiB fill); a new ray batch every step", "events": "CUDA events per step on the launch stream, max over ranks",
+                       "step": "TetrahedraNerf.forward (training mode) -> MSE loss -> backward -> (N>1: gradient all-reduce) -> RAdam step"},
+            "roofline": {"kernel": "whole training step", "bound": "tensor", "unit": "TFLOP/s", "achieved": ach, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],
+                         "peak_src": pk["src"] + " bf16 sustained", "frac": ach / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), "traffic": None,
+                         "note": "algorithmic fp32-equivalent FLOPs of SURVEY §8d (fwd coarse + fine, bwd 2 x fine); bf16x3 issues 3 MMAs per MAC and the backward recomputes the fine forward"},
+            "unfused_reference_sequence": {"ms_per_step": ms_unfused / usteps, "steps": usteps,
+                                           "what": "same model, TETRANERF_B200_UNFUSED_TRAIN=1: the reference's op sequence on this repo's unfused CUDA ops + torch fp32 MLP + autograd"},
+            "speedup_vs_unfused": (ms_unfused / usteps) / (ms_total / args.steps),
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": R * 36, "d2h_bytes_per_step": 4,
+                    "api": "TetrahedraNerf.forward(RayBundle) + get_loss_dict + backward + optimizer, pinned host rays/targets in, loss out"},
+            "gpu_launches": int(launches), "clocks": sampler.result(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -545,8 +545,8 @@ def render_train(mesh: OracleMesh, field: torch.Tensor, params: Dict[str, torch.
     mi = torch.clamp(torch.searchsorted(cumw, torch.ones((weights.shape[0], 1)) * 0.5, side="left"), 0, steps.shape[-1] - 1)
     depth_r = torch.gather(steps, dim=-1, index=mi)
     idx = torch.nonzero(ray_mask).flatten()
-    rgb = torch.ones((R, 3), dtype=torch.float32).index_copy(0, idx, rgb_r)
-    acc = torch.zeros((R, 1), dtype=torch.float32).index_copy(0, idx, accum)
-    depth = torch.full((R, 1), cfg.far_plane, dtype=torch.float32).index_copy(0, idx, depth_r)
+    rgb = torch.ones((R, 3), dtype=rgb_r.dtype).index_copy(0, idx, rgb_r)  # (dtype follows the inputs: tests also run this in float64)
+    acc = torch.zeros((R, 1), dtype=rgb_r.dtype).index_copy(0, idx, accum)
+    depth = torch.full((R, 1), cfg.far_plane, dtype=depth_r.dtype).index_copy(0, idx, depth_r)
     return {"rgb": rgb, "accumulation": acc, "depth": depth, "ray_mask": ray_mask,
             "aux": {"fine_euclid": euclid.detach(), "sigmas": sigmas.detach(), "colors": colors.detach(), "weights": weights.detach(), "matched": tc}}

@@ -103,3 +103,26 @@ def test_th_file_loader_and_dataparser_transform(tmp_path, small_mesh):
     m_no_pipe = M.TetrahedraNerf(cfg)
     with pytest.raises(RuntimeError, match="dataparser_scale"):
         m_no_pipe._init_tetrahedra()  # model.py:352-356
+
+
+def test_image_metrics_and_appearance_embedding_modules():
+    """ns-eval / steps_per_eval_image call get_image_metrics_and_images; appearance_embed_dim > 0 must create the embedding and
+    widen mlp_head (reference model.py:440-446, 676-713)"""
+    import torch
+
+    from tetranerf.nerfstudio import model as M
+
+    cfg = M.TetrahedraNerfConfig(num_tetrahedra_vertices=10, num_tetrahedra_cells=5, appearance_embed_dim=8)
+    m = M.TetrahedraNerf(cfg, num_train_data=7)
+    assert m.appearance_embedding.weight.shape == (7, 8)
+    assert m.mlp_head.layers[0].weight.shape == (128, 128 + 27 + 8)
+    assert not m._fused_supported()
+    g = torch.Generator().manual_seed(0)
+    img = torch.rand((32, 40, 3), generator=g)
+    out = {"rgb": (img + 0.05 * torch.rand((32, 40, 3), generator=g)).clamp(0, 1), "accumulation": torch.rand((32, 40, 1), generator=g),
+           "depth": 2 + torch.rand((32, 40, 1), generator=g)}
+    metrics, images = m.get_image_metrics_and_images(out, {"image": img})
+    assert 20 < metrics["psnr"] < 40 and 0.5 < metrics["nerfstudio_ssim"] <= 1.0
+    assert images["img"].shape == (32, 80, 3) and images["accumulation"].shape == (32, 40, 3) and images["depth"].shape == (32, 40, 3)
+    same, _ = m.get_image_metrics_and_images({**out, "rgb": img}, {"image": img})
+    assert same["nerfstudio_ssim"] > 0.9999

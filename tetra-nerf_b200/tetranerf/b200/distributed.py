@@ -46,3 +46,27 @@ def sharded_render(render_fn: Callable[[torch.Tensor, torch.Tensor], Dict[str, t
     full = gathered[rows]
     return {"rgb": full[:, 0:3].contiguous(), "accumulation": full[:, 3:4].contiguous(), "depth": full[:, 4:5].contiguous(),
             "ray_mask": full[:, 5] > 0.5}
+
+
+def average_gradients(parameters, group=None) -> None:
+    """DDP semantics of the reference's only multi-GPU mechanism (tetranerf/nerfstudio/pipeline.py:53-58 wraps the model in
+    DistributedDataParallel): every rank draws its own ray batch, the gradients are AVERAGED over the ranks before the optimizer step --
+    `tetrahedra_field.grad` ([64,V]: 77 MB at 300k vertices) and the twelve MLP gradients, packed into one flat buffer and reduced with a
+    single all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).  The fused training step produces all gradients at the end of
+    one backward op, so there is nothing to bucket or overlap inside it."""
+    if not dist.is_available() or not dist.is_initialized():
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

@@ -12,8 +12,9 @@ the work happens:
     interpolate_values -> torch MLPs -> renderers) is kept, on top of our CUDA ops, so that autograd
     reaches `tetrahedra_field` and the MLP weights exactly as it does upstream.
 
-Out of this path's scope and therefore absent: image metrics (PSNR/SSIM/LPIPS, reference :474-477,676-713),
-the unused occupancy field (:98,256-265) and appearance embeddings.  nerfstudio itself is imported when it is
+Evaluation images / metrics (`get_image_metrics_and_images`, reference :676-713) are provided with PSNR and SSIM computed in torch
+(torchmetrics / LPIPS are used when nerfstudio and its dependencies are installed); appearance embeddings (reference :440-446,
+608-620) run on the unfused path.  Out of scope and absent: the unused occupancy field (:98,256-265).  nerfstudio itself is imported when it is
 installed; otherwise the minimal look-alikes of `_ns_compat` are used.
 """
 from __future__ import annotations
@@ -241,8 +242,11 @@ class TetrahedraNerf(Model):
             self.position_encoding = lambda x: x
         self.direction_encoding = NeRFEncoding(in_dim=3, num_frequencies=4, min_freq_exp=0.0, max_freq_exp=4.0, include_input=True)
         self.mlp_base = MLP(in_dim=in_dim, num_layers=self.config.num_density_layers, layer_width=self.config.hidden_size, out_activation=nn.ReLU())
-        self.mlp_head = MLP(in_dim=self.mlp_base.get_out_dim() + self.direction_encoding.get_out_dim(), num_layers=self.config.num_color_layers,
-                            layer_width=self.config.hidden_size, out_activation=nn.ReLU())
+        head_in = self.mlp_base.get_out_dim() + self.direction_encoding.get_out_dim()
+        if self.config.appearance_embed_dim > 0:  # reference :440-446
+            self.appearance_embedding = nn.Embedding(self.num_train_data, self.config.appearance_embed_dim)
+            head_in += self.config.appearance_embed_dim
+        self.mlp_head = MLP(in_dim=head_in, num_layers=self.config.num_color_layers, layer_width=self.config.hidden_size, out_activation=nn.ReLU())
         self.field_output_color = RGBFieldHead(in_dim=self.mlp_head.get_out_dim())
         self.field_output_density = DensityFieldHead(in_dim=self.mlp_base.get_out_dim())
         if self.config.use_biased_sampler:
@@ -348,7 +352,14 @@ class TetrahedraNerf(Model):
                 features = self._field_at(tracer, traced, ray_mask, (samples.frustums.ends + samples.frustums.starts) / 2)
             base = self.mlp_base(self.position_encoding(features))
             sigmas = self.field_output_density(base)
-            colors = self.field_output_color(self.mlp_head(torch.cat([self.direction_encoding(samples.frustums.directions), base], dim=-1)))
+            head_in = [self.direction_encoding(samples.frustums.directions), base]
+            if self.config.appearance_embed_dim > 0:  # reference :608-620
+                if self.training:
+                    assert samples.camera_indices is not None
+                    head_in.append(self.appearance_embedding(samples.camera_indices.squeeze()))
+                else:
+                    head_in.append(torch.ones((*base.shape[:-1], self.config.appearance_embed_dim), device=base.device) * self.appearance_embedding.weight.mean(dim=0))
+            colors = self.field_output_color(self.mlp_head(torch.cat(head_in, dim=-1)))
             if self.config.use_gradient_scaling:
                 colors, sigmas, _ = GradientScaler.apply(colors, sigmas, samples.spacing_ends + samples.spacing_starts)
             weights = samples.get_weights(sigmas)
@@ -360,3 +371,84 @@ class TetrahedraNerf(Model):
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
         image = batch["image"].to(outputs["rgb"].device)
         return scale_dict({"rgb_loss": self.rgb_loss(image, outputs["rgb"])}, self.config.loss_coefficients)
+
+    # ---- evaluation images and metrics (reference :676-713) --------------------------------------------------------------------------
+    def get_image_metrics_and_images(self, outputs: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor]):
+        image = batch["image"].to(outputs["rgb"].device)
+        rgb = outputs["rgb"]
+        acc = _apply_colormap(outputs["accumulation"])
+        depth = _apply_depth_colormap(outputs["depth"], accumulation=outputs["accumulation"])
+        images = {"img": torch.cat([image, rgb], dim=1), "accumulation": torch.cat([acc], dim=1), "depth": torch.cat([depth], dim=1)}
+        # [H, W, C] -> [1, C, H, W]
+        im, pr = torch.moveaxis(image, -1, 0)[None, ...], torch.moveaxis(rgb, -1, 0)[None, ...]
+        metrics = {"psnr": float(_psnr(im, pr)), "nerfstudio_ssim": float(_ssim(im, pr))}
+        lp = _lpips(im, pr)
+        if lp is not None:
+            metrics["lpips"] = float(lp)
+        return metrics, images
+
+
+def _psnr(a: torch.Tensor, b: torch.Tensor, data_range: float = 1.0) -> torch.Tensor:
+    """torchmetrics PeakSignalNoiseRatio(data_range=1.0) (reference :470)"""
+    mse = torch.mean((a - b) ** 2)
+    return 10.0 * torch.log10(data_range**2 / mse)
+
+
+def _ssim(a: torch.Tensor, b: torch.Tensor, data_range: float = 1.0, kernel: int = 11, sigma: float = 1.5, k1: float = 0.01, k2: float = 0.03) -> torch.Tensor:
+    """torchmetrics.functional.structural_similarity_index_measure with its defaults (Gaussian 11x11, sigma 1.5), [N,C,H,W] in [0,1]"""
+    c = a.shape[1]
+    x = torch.arange(kernel, dtype=a.dtype, device=a.device) - (kernel - 1) / 2
+    g = torch.exp(-(x**2) / (2 * sigma**2))
+    g = (g / g.sum())[:, None] * (g / g.sum())[None, :]
+    w = g.expand(c, 1, kernel, kernel).contiguous()
+    pad = (kernel - 1) // 2
+    ap, bp = (torch.nn.functional.pad(t, (pad, pad, pad, pad), mode="reflect") for t in (a, b))
+
+    def f(t):
+        return torch.nn.functional.conv2d(t, w, groups=c)
+
+    mu_a, mu_b = f(ap), f(bp)
+    s_aa, s_bb, s_ab = f(ap * ap) - mu_a**2, f(bp * bp) - mu_b**2, f(ap * bp) - mu_a * mu_b
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    ssim = ((2 * mu_a * mu_b + c1) * (2 * s_ab + c2)) / ((mu_a**2 + mu_b**2 + c1) * (s_aa + s_bb + c2))
+    return ssim.mean()
+
+
+_LPIPS = None
+
+
+def _lpips(a, b):
+    """LearnedPerceptualImagePatchSimilarity (reference :474) when torchmetrics + its weights are available; None otherwise"""
+    global _LPIPS
+    if _LPIPS is False:
+        return None
+    try:
+        if _LPIPS is None:
+            from torchmetrics.image.lpip import LearnedPerceptualImagePatchSimilarity
+
+            _LPIPS = LearnedPerceptualImagePatchSimilarity().to(a.device)
+        return _LPIPS(a, b)
+    except Exception:  # not installed / no pretrained weights offline
+        _LPIPS = False
+        return None
+
+
+def _apply_colormap(x: torch.Tensor) -> torch.Tensor:
+    try:
+        from nerfstudio.utils import colormaps
+
+        return colormaps.apply_colormap(x)
+    except ImportError:
+        return torch.nan_to_num(x, 0.0).clamp(0, 1).expand(*x.shape[:-1], 3)
+
+
+def _apply_depth_colormap(depth: torch.Tensor, accumulation: Optional[torch.Tensor] = None) -> torch.Tensor:
+    try:
+        from nerfstudio.utils import colormaps
+
+        return colormaps.apply_depth_colormap(depth, accumulation=accumulation)
+    except ImportError:
+        near, far = float(depth.min()), float(depth.max())
+        d = ((depth - near) / (far - near + 1e-10)).clamp(0, 1)
+        img = torch.nan_to_num(d, 0.0).expand(*d.shape[:-1], 3)
+        return img * accumulation + (1 - accumulation) if accumulation is not None else img
