@@ -518,6 +518,27 @@ def run_train(args, rank, world, dev, V, C, field, params, dist):
     sampler.join(timeout=2)
     usteps = max(3, args.steps // 4)
     ms_unfused, _ = run("1", usteps, 3, False)
+    # per-kernel breakdown of one fused step (CUDA events inside the library), plus torch-side pieces timed separately
+    os.environ["TETRANERF_B200_UNFUSED_TRAIN"] = "0"
+    model = make_model()
+    opt = torch.optim.RAdam(model.parameters(), lr=1e-3)
+    fr = model._fused_renderer()
+    fr.set_profiling(True)
+    kern = {}
+    for i in range(4):
+        b = devb[i]
+        out = model(tnm.RayBundle(origins=b[:, 0:3].contiguous(), directions=b[:, 3:6].contiguous()))
+        loss = model.get_loss_dict(out, {"image": b[:, 6:9]})["rgb_loss"]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); opt.step(); e1.record()
+        torch.cuda.synchronize(dev)
+        if i >= 2:
+            for n, v in {**fr.kernel_timings_ms(), **fr.backward_timings_ms(), "optimizer_radam": e0.elapsed_time(e1)}.items():
+                kern[n] = kern.get(n, 0.0) + v / 2
+    fr.set_profiling(False)
+    del model, opt
     if rank == 0:
         pk = peaks()
         total = world * R * args.steps
@@ -537,7 +558,7 @@ def run_train(args, rank, world, dev, V, C, field, params, dist):
                          "note": "algorithmic fp32-equivalent FLOPs of SURVEY §8d (fwd coarse + fine, bwd 2 x fine); bf16x3 issues 3 MMAs per MAC and the backward recomputes the fine forward"},
             "unfused_reference_sequence": {"ms_per_step": ms_unfused / usteps, "steps": usteps,
                                            "what": "same model, TETRANERF_B200_UNFUSED_TRAIN=1: the reference's op sequence on this repo's unfused CUDA ops + torch fp32 MLP + autograd"},
-            "speedup_vs_unfused": (ms_unfused / usteps) / (ms_total / args.steps),
+            "speedup_vs_unfused": (ms_unfused / usteps) / (ms_total / args.steps), "kernel_ms": kern,
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": R * 36, "d2h_bytes_per_step": 4,
                     "api": "TetrahedraNerf.forward(RayBundle) + get_loss_dict + backward + optimizer, pinned host rays/targets in, loss out"},
             "gpu_launches": int(launches), "clocks": sampler.result(),

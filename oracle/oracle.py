@@ -493,10 +493,13 @@ def interpolate_torch(vertex_indices, bary, field):
 
 
 def render_train(mesh: OracleMesh, field: torch.Tensor, params: Dict[str, torch.Tensor], origins, directions, cfg: RenderConfig,
-                 jitter_coarse=None, jitter_fine=None, use_gradient_scaling: bool = False, nthreads: int = 0):
+                 jitter_coarse=None, jitter_fine=None, use_gradient_scaling: bool = False, nthreads: int = 0, fine_euclid=None):
     """TetrahedraNerf.get_outputs in TRAINING mode (model.py:520-662) in differentiable torch-CPU fp32: `field` and the entries of `params`
     may require grad.  jitter_coarse f32[R,S_c+1] / jitter_fine f32[R,S_f+1] are the uniform draws of the two stratified samplers, indexed by
-    RAY (the reference draws them with torch.rand on the non-empty rays).  Training-mode renderer: white background, no nan_to_num / clamp."""
+    RAY (the reference draws them with torch.rand on the non-empty rays).  Training-mode renderer: white background, no nan_to_num / clamp.
+    fine_euclid f32[R',S2+1] (non-empty rays, in ray order): use THESE fine-pass bin edges instead of running the coarse pass and the PDF
+    sampler -- the bins are detached (non-differentiable) in the reference, so the gradient arithmetic of an implementation can be checked
+    at the implementation's own sample positions, which move by ~1e-6 between any two fp32 PDF inversions."""
     o = torch.as_tensor(np.asarray(origins), dtype=torch.float32).reshape(-1, 3)
     d = torch.as_tensor(np.asarray(directions), dtype=torch.float32).reshape(-1, 3)
     R = o.shape[0]
@@ -519,7 +522,11 @@ def render_train(mesh: OracleMesh, field: torch.Tensor, params: Dict[str, torch.
         return find_visited_cells(trm["num_visited_cells"], trm["visited_cells"], trm["barycentric_coordinates"], trm["hit_distances"],
                                   trm["vertex_indices"], dist.detach().numpy(), nthreads=nthreads)
 
-    with torch.no_grad():  # the coarse pass only feeds the (detached) PDF bins
+    if fine_euclid is not None:
+        euclid = torch.as_tensor(fine_euclid, dtype=torch.float32)
+        sbins = (euclid - nears_r) / (fars_r - nears_r)
+    else:
+      with torch.no_grad():  # the coarse pass only feeds the (detached) PDF bins
         euclid, sbins = coarse_bins(cfg, nears_r, fars_r, num_visited[ray_mask], hd[ray_mask], jc)
         tc = match(euclid)
         fv = interpolate_torch(tc["vertex_indices"], tc["barycentric_coordinates"], field.detach())

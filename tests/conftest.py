@@ -32,3 +32,19 @@ def medium_mesh():
     from tetranerf.b200 import synthetic as syn
 
     return syn.delaunay_mesh(20000, seed=5)
+
+
+# the bit-identical implementations of trace_rays and how to force each one: (walk_min_rays, solo range, quad range)
+TRACE_IMPLS = {
+    "walk": (0, (1, 0), (1, 0)),                                  # adjacency walk, 32 rays per warp
+    "walk_solo": (2**32 - 1, (0, 2**32 - 1), (1, 0)),             # adjacency walk, one ray per warp
+    "walk_quad": (2**32 - 1, (1, 0), (0, 2**32 - 1)),             # adjacency walk, 8 rays per warp (4 lanes per ray)
+    "bvh": (2**32 - 1, (1, 0), (1, 0)),                           # warp-per-ray all-hits BVH gather
+}
+
+
+def force_trace_impl(tracer, name):
+    w = TRACE_IMPLS[name]
+    tracer.set_walk_min_rays(w[0])
+    tracer.set_walk_solo_range(*w[1])
+    tracer.set_walk_quad_range(*w[2])

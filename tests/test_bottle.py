@@ -98,7 +98,7 @@ def test_bottle_reference_invariant(bottle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("impl", ["walk", "walk_solo", "bvh"])
+@pytest.mark.parametrize("impl", ["walk", "walk_solo", "walk_quad", "bvh"])
 def test_bottle_gpu_equals_oracle(bottle, impl):
     from tetranerf import cpp
 
@@ -106,8 +106,9 @@ def test_bottle_gpu_equals_oracle(bottle, impl):
     V, C = bottle
     tr = cpp.TetrahedraTracer(dev)
     tr.load_tetrahedra(torch.from_numpy(V).to(dev), torch.from_numpy(C).to(dev))
-    w = {"walk": (0, 1, 0), "walk_solo": (2**32 - 1, 0, 2**32 - 1), "bvh": (2**32 - 1, 1, 0)}[impl]
-    tr.set_walk_min_rays(w[0]); tr.set_walk_solo_range(w[1], w[2])
+    from conftest import force_trace_impl
+
+    force_trace_impl(tr, impl)
     o, d = reference_camera_rays()
     o2 = (o + np.random.default_rng(0).normal(0, 0.3, o.shape)).astype(np.float32)  # a second, incoherent bundle aimed at the bottle
     d2 = -o2 + np.random.default_rng(1).normal(0, 0.03, o.shape); d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)

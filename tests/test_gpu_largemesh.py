@@ -12,7 +12,7 @@ from tetranerf.b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
 KEYS = ["num_visited_cells", "visited_cells", "vertex_indices", "hit_distances", "barycentric_coordinates"]
-IMPLS = {"walk": (0, 1, 0), "walk_solo": (2**32 - 1, 0, 2**32 - 1), "bvh": (2**32 - 1, 1, 0)}
+from conftest import TRACE_IMPLS as IMPLS, force_trace_impl
 
 
 def _tracer(V, C):
@@ -24,9 +24,7 @@ def _tracer(V, C):
 
 
 def _gpu(tr, impl, o, d, M):
-    w = IMPLS[impl]
-    tr.set_walk_min_rays(w[0])
-    tr.set_walk_solo_range(w[1], w[2])
+    force_trace_impl(tr, impl)
     out = tr.trace_rays(torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), M)
     tr.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items()}

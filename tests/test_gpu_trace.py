@@ -12,15 +12,17 @@ DEV = torch.device("cuda:0")
 KEYS = ["num_visited_cells", "visited_cells", "vertex_indices", "hit_distances", "barycentric_coordinates"]
 
 
-WALK = (0, 1, 0)  # set by the autouse fixture: (walk_min_rays, solo range lo, hi)
+from conftest import TRACE_IMPLS, force_trace_impl
+
+IMPL = "walk"  # set by the autouse fixture
 
 
-@pytest.fixture(autouse=True, params=["walk", "walk_solo", "bvh"])
+@pytest.fixture(autouse=True, params=list(TRACE_IMPLS))
 def trace_impl(request):
-    """every test of this file runs against all three (bit-identical) implementations of trace_rays: adjacency walk with
-    32 rays per warp, adjacency walk with one ray per warp, warp-per-ray BVH gather"""
-    global WALK
-    WALK = {"walk": (0, 1, 0), "walk_solo": (2**32 - 1, 0, 2**32 - 1), "bvh": (2**32 - 1, 1, 0)}[request.param]
+    """every test of this file runs against all four (bit-identical) implementations of trace_rays: adjacency walk with
+    32 / 8 / 1 rays per warp, warp-per-ray BVH gather"""
+    global IMPL
+    IMPL = request.param
     yield request.param
 
 
@@ -29,8 +31,7 @@ def make_tracer(V, C):
 
     tr = cpp.TetrahedraTracer(DEV)
     tr.load_tetrahedra(torch.from_numpy(V).to(DEV), torch.from_numpy(C).to(DEV))
-    tr.set_walk_min_rays(WALK[0])
-    tr.set_walk_solo_range(WALK[1], WALK[2])
+    force_trace_impl(tr, IMPL)
     return tr
 
 
@@ -249,7 +250,7 @@ def test_walk_fast_path_classification(small_mesh):
     g = gpu_trace(tr, o, d, 512)
     walkable, listed = tr.trace_stats()
     assert walkable
-    if WALK[0] == 0 or WALK[1] <= WALK[2]:  # either form of the walk
+    if IMPL != "bvh":  # any form of the walk
         assert 0 < listed < 0.15 * len(o), listed
     assert_same(g, orc.OracleMesh(V, C).trace_rays(o, d, 512))
 

@@ -151,6 +151,13 @@ extern "C" int tn_set_walk_solo_range(tn_tracer *h, uint32_t lo, uint32_t hi) {
     h->walk_solo_max_rays = hi;
     return TN_OK;
 }
+// batches below walk_min_rays with lo <= rays <= hi take the 8-rays-per-warp form of the walk (lo > hi = never); checked before the solo range
+extern "C" int tn_set_walk_quad_range(tn_tracer *h, uint32_t lo, uint32_t hi) {
+    if (!h) return tn::fail(TN_ERR_ARG, "null tracer");
+    h->walk_quad_min_rays = lo;
+    h->walk_quad_max_rays = hi;
+    return TN_OK;
+}
 static uint32_t g_last_exact = 0;
 extern "C" uint32_t tn_debug_last_exact_count(void) { return g_last_exact; }
 // test hook: (walkable mesh?, number of rays the last trace_rays call handed to the exact stage); synchronises the device

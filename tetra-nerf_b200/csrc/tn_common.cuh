@@ -107,6 +107,9 @@ struct tn_tracer {
     // batches of [walk_solo_min_rays, walk_solo_max_rays] rays (below walk_min_rays) take the one-ray-per-warp walk: measured
     // (profiles/r1_trace_sweep.json) 0.32 / 0.51 ms at 4096 / 8192 rays against the gather's 0.29 / 0.56 ms
     uint32_t walk_solo_min_rays = 6144, walk_solo_max_rays = 0xFFFFFFFFu;
+    // batches of [walk_quad_min_rays, walk_quad_max_rays] rays (below walk_min_rays; checked before the solo range) take the walk with
+    // 8 rays per warp, 4 cooperating lanes per ray (default: off until measured; see profiles/r2_trace_sweep.json)
+    uint32_t walk_quad_min_rays = 1, walk_quad_max_rays = 0;
     uint64_t launches = 0;
     tn::RenderState *render = nullptr;
 };
@@ -128,7 +131,7 @@ int build_faces_device(const float *d_xyz, uint32_t V, const uint32_t *d_cells, 
 void free_mesh(tn_tracer *h);
 void free_render(tn_tracer *h);
 int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
-                float *dist, uint32_t *verts, unsigned long long *keys, uint32_t *list, uint32_t *list_count, bool solo, cudaStream_t s);
+                float *dist, uint32_t *verts, unsigned long long *keys, uint32_t *list, uint32_t *list_count, int kind, cudaStream_t s);
 int launch_tail_fill(tn_tracer *h, uint32_t R, uint32_t M, const uint32_t *num, uint32_t *cells, float *bary, float *dist, uint32_t *verts,
                      cudaStream_t s);
 int launch_prefetch(tn_tracer *h, const void *const *extra, const size_t *extra_bytes, int nextra, cudaStream_t s);

@@ -62,6 +62,7 @@ struct RenderState {
     // optional per-kernel timing (bench.py roofline): events around the 6 kernels of tn_render
     bool profile = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evb[4] = {nullptr, nullptr, nullptr, nullptr};  // backward: start | composite_bwd | mlp_bwd | finalize
 };
 
 static void free_ws(RenderState *r) {
@@ -82,6 +83,7 @@ void free_render(tn_tracer *h) {
     cudaFree(r->wimg_bwd); cudaFree(r->sbins_f); cudaFree(r->enc); cudaFree(r->dout); cudaFree(r->gshadow); cudaFree(r->gw); cudaFree(r->g_dirbias);
     cudaFree(r->scratch);
     for (auto &e : r->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : r->evb) if (e) cudaEventDestroy(e);
     delete r;
     h->render = nullptr;
 }
@@ -819,7 +821,9 @@ extern "C" int tn_render_train_backward(tn_tracer *h, const float *d_grad_rgb, c
     const size_t smem_cb = SAMPLE_WARPS * sizeof(float) * 4 * ((size_t)S2 + 2);
     TN_CUDA(cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
     const uint32_t gridR = (R + SAMPLE_WARPS - 1) / SAMPLE_WARPS;
+    if (r->profile) cudaEventRecord(r->evb[0], s);
     k_composite_bwd<<<gridR, SAMPLE_WARPS * 32, smem_cb, s>>>(cb);
+    if (r->profile) cudaEventRecord(r->evb[1], s);
     MlpBwdParams bp{};
     bp.n_active = r->n_active; bp.S = S2; bp.vi = r->vi_f; bp.bary = r->bary_f; bp.fshadow = r->fshadow; bp.wimg = r->wimg_bwd;
     bp.bias = r->bias; bp.head = r->head; bp.dirbias = r->dirbias; bp.dout = r->dout; bp.scratch = r->scratch; bp.gshadow = r->gshadow;
@@ -827,6 +831,7 @@ extern "C" int tn_render_train_backward(tn_tracer *h, const float *d_grad_rgb, c
     TN_CUDA(cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
     const uint32_t tiles = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
     k_mlp_bwd<<<std::min<uint32_t>(tiles, (uint32_t)sms), BWD_THREADS, BWD_SMEM_BYTES, s>>>(bp);
+    if (r->profile) cudaEventRecord(r->evb[2], s);
     k_dirbias_grads<<<128, 32, 0, s>>>(r->n_active, r->g_dirbias, r->enc, r->gw);
     GradOut go{};
     for (int i = 0; i < 12; ++i) {
@@ -835,6 +840,7 @@ extern "C" int tn_render_train_backward(tn_tracer *h, const float *d_grad_rgb, c
     }
     k_scatter_grads<<<(128 * 155 + 255) / 256, 256, 0, s>>>(r->gw, go);
     k_transpose_v64<<<(V + 31) / 32, dim3(32, 8), 0, s>>>(r->gshadow, d_grad_field, V);
+    if (r->profile) cudaEventRecord(r->evb[3], s);
     h->launches += 5;
     TN_CUDA(cudaGetLastError());
     return TN_OK;
@@ -859,6 +865,7 @@ extern "C" int tn_render_set_profiling(tn_tracer *h, int enable) {
     DeviceGuard g(h->device);
     RenderState *r = state(h);
     if (enable) for (auto &e : r->ev) if (!e) TN_CUDA(cudaEventCreate(&e));
+    if (enable) for (auto &e : r->evb) if (!e) TN_CUDA(cudaEventCreate(&e));
     r->profile = enable != 0;
     return TN_OK;
 }
@@ -868,6 +875,16 @@ extern "C" int tn_render_get_timings(tn_tracer *h, float *ms6) {
     RenderState *r = h->render;
     TN_CUDA(cudaEventSynchronize(r->ev[6]));
     for (int i = 0; i < 6; ++i) TN_CUDA(cudaEventElapsedTime(&ms6[i], r->ev[i], r->ev[i + 1]));
+    return TN_OK;
+}
+
+// per-kernel timing of the LAST tn_render_train_backward call: ms3 = composite_bwd, mlp_bwd, finalize (memsets excluded)
+extern "C" int tn_render_get_backward_timings(tn_tracer *h, float *ms3) {
+    if (!h || !h->render || !h->render->profile) return fail(TN_ERR_STATE, "profiling is not enabled");
+    DeviceGuard g(h->device);
+    RenderState *r = h->render;
+    TN_CUDA(cudaEventSynchronize(r->evb[3]));
+    for (int i = 0; i < 3; ++i) TN_CUDA(cudaEventElapsedTime(&ms3[i], r->evb[i], r->evb[i + 1]));
     return TN_OK;
 }
 

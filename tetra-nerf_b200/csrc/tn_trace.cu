@@ -489,8 +489,9 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
     // walk / solo walk (the tests exercise all three through the setters).
     static const int walk_env = [] { const char *e = getenv("TETRANERF_B200_WALK"); return e ? atoi(e) : -1; }();
     const bool thread_walk = walk_env >= 0 ? walk_env == 1 : R >= h->walk_min_rays;
-    const bool solo_walk = walk_env >= 0 ? walk_env == 2 : (!thread_walk && R >= h->walk_solo_min_rays && R <= h->walk_solo_max_rays);
-    if (mode == 0 && h->mesh.walkable && M >= 4 && (thread_walk || solo_walk)) {
+    const bool quad_walk = walk_env >= 0 ? walk_env == 3 : (!thread_walk && R >= h->walk_quad_min_rays && R <= h->walk_quad_max_rays);
+    const bool solo_walk = walk_env >= 0 ? walk_env == 2 : (!thread_walk && !quad_walk && R >= h->walk_solo_min_rays && R <= h->walk_solo_max_rays);
+    if (mode == 0 && h->mesh.walkable && M >= 4 && (thread_walk || solo_walk || quad_walk)) {
         // fast path: adjacency walk (tn_walk.cu); rays it cannot certify are listed for the exact stage below
         const size_t need = (size_t)R * M;
         if (h->walk_keys_cap < need) {
@@ -507,7 +508,7 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
         }
         uint32_t *list_count = reinterpret_cast<uint32_t *>(h->d_flags + 2);
         TN_CUDA(cudaMemsetAsync(list_count, 0, 2 * sizeof(uint32_t), s));
-        int rc = launch_walk(h, o, d, R, M, num, cells, bary, dist, verts, h->d_walk_keys, h->d_ovf_list, list_count, solo_walk && !thread_walk, s);
+        int rc = launch_walk(h, o, d, R, M, num, cells, bary, dist, verts, h->d_walk_keys, h->d_ovf_list, list_count, thread_walk ? 0 : (quad_walk ? 2 : 1), s);
         if (rc) return rc;
         p.dense = 0;
         p.hcap = M + 128; p.scap = 4096; p.lcap = M > 512 ? M / 2 : 320;

@@ -362,6 +362,190 @@ __global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
     }
 }
 
+// ---- eight rays per warp, four cooperating lanes per ray ("quad") -----------------------------------------------------------------
+// Same outputs, classification and fallbacks as k_walk / k_walk_coop (the same algorithm).  A 4096-ray batch is 512 warps = 3.5 per
+// SM: the walk is a serial chain of L2 round trips per ray, so what matters at this size is how many instructions are issued per
+// step and how many chains are in flight per scheduler.  One ray per warp (k_walk_coop) issues a full warp instruction stream per
+// ray (28 warps per SM fight for issue slots); 32 rays per warp (k_walk) leaves 128 warps for 148 SMs.  Here a warp instruction
+// stream serves 8 rays: lane j of a quad owns vertex j and the face opposite to it, exactly as in k_walk_coop.
+constexpr int QUAD_WARPS = 2;  // 64 threads = 16 rays per block: 256 blocks for 4096 rays, spread over all SMs
+__global__ void __launch_bounds__(QUAD_WARPS * 32) k_walk_quad(const WalkParams p) {
+    __shared__ uint32_t s_stack[QUAD_WARPS * 8][8 * TN_MAX_LEVELS + 8];
+    constexpr unsigned FULLM = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lq = lane & 3u, gbase = lane & ~3u, grp = lane >> 2;  // lane inside the quad, first lane of the quad, quad inside the warp
+    const uint32_t ray = (blockIdx.x * QUAD_WARPS + warp) * 8u + grp;
+    const bool in_range = ray < p.R;
+    const uint32_t rr = in_range ? ray : 0u;
+    uint32_t *stack = s_stack[warp * 8 + grp];
+    const float ox = p.o[3 * (size_t)rr], oy = p.o[3 * (size_t)rr + 1], oz = p.o[3 * (size_t)rr + 2];
+    const float dx = p.d[3 * (size_t)rr], dy = p.d[3 * (size_t)rr + 1], dz = p.d[3 * (size_t)rr + 2];
+    const RaySetup rs = ray_setup(ox, oy, oz, dx, dy, dz);
+    const size_t row = (size_t)rr * p.M;
+    bool live = in_range && rs.valid;  // quad-uniform
+    if (in_range && !rs.valid && lq == 0) p.num[ray] = 0;
+
+    // ---- hull entry: closest hit over the hull faces; lane lq takes children lq and lq + 4 of the popped node ----
+    u64 best = ~0ull;
+    float bu = 0.f, bv = 0.f;
+    uint32_t btet = TN_EMPTY, bj = 0, hullhits = 0;
+    {
+        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+        const float pad = 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + p.absmax);
+        int sp = live ? 1 : 0;
+        if (live && lq == 0) stack[0] = (uint32_t)(p.hlv.nlevels - 1) << 28;
+        __syncwarp();
+        while (__any_sync(FULLM, sp > 0)) {
+            const bool act = sp > 0;
+            uint32_t e = 0;
+            if (act) e = stack[--sp];
+            __syncwarp();  // every lane of the quad has read the entry before it can be overwritten
+            const uint32_t cl = act ? (e >> 28) - 1u : 0u, cbase = (e & 0x0FFFFFFFu) << TN_FAN_LOG2;
+            const uint32_t nc = act ? min(TN_FAN, p.hlv.count[cl] - cbase) : 0u;
+            bool hit[2] = {false, false};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t c = lq + 4u * (uint32_t)k;
+                if (c < nc) {
+                    const float4 *np = p.hull_nodes + 2 * (size_t)(p.hlv.offset[cl] + cbase + c);
+                    hit[k] = slab(__ldg(np), __ldg(np + 1), ox, oy, oz, ix, iy, iz, pad);
+                }
+            }
+            const uint32_t m0 = (__ballot_sync(FULLM, hit[0]) >> gbase) & 0xFu, m1 = (__ballot_sync(FULLM, hit[1]) >> gbase) & 0xFu;
+            if (act && cl != 0) {
+                if (hit[0]) stack[sp + __popc(m0 & ((1u << lq) - 1u))] = (cl << 28) | (cbase + lq);
+                if (hit[1]) stack[sp + __popc(m0) + __popc(m1 & ((1u << lq) - 1u))] = (cl << 28) | (cbase + lq + 4u);
+                sp += __popc(m0) + __popc(m1);
+            } else if (act) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (!hit[k]) continue;  // a hull tetrahedron: its hull faces are owned, their stored winding is this rotation
+                    const uint32_t c = lq + 4u * (uint32_t)k;
+                    const float4 *lp = reinterpret_cast<const float4 *>(p.hull_leaves + cbase + c);
+                    const float4 v0 = __ldg(lp), v1 = __ldg(lp + 1), v2 = __ldg(lp + 2), v3 = __ldg(lp + 3);
+                    const uint32_t f[4] = {__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w), __float_as_uint(v3.w)};
+                    const Sheared sv[4] = {shear(rs, v0.x, v0.y, v0.z), shear(rs, v1.x, v1.y, v1.z), shear(rs, v2.x, v2.y, v2.z), shear(rs, v3.x, v3.y, v3.z)};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (!(f[j] & TN_FACE_HULL)) continue;
+                        float t, u, v;
+                        if (tri_test(sv[(j + 1) & 3], sv[(j + 2) & 3], sv[(j + 3) & 3], t, u, v)) {
+                            const u64 key = ((u64)__float_as_uint(t) << 32) | (f[j] & TN_FACE_MASK);
+                            hullhits++;
+                            if (key < best) { best = key; bu = u; bv = v; btet = p.hull_tet[cbase + c]; bj = (uint32_t)j; }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // the smallest key over the quad wins (keys are unique: a face is tested by one lane only)
+        u64 m = best;
+#pragma unroll
+        for (int o = 2; o >= 1; o >>= 1) {
+            const u64 other = __shfl_xor_sync(FULLM, m, o);
+            m = other < m ? other : m;
+            hullhits += __shfl_xor_sync(FULLM, hullhits, o);
+        }
+        const uint32_t winm = (__ballot_sync(FULLM, best == m) >> gbase) & 0xFu;
+        const uint32_t win = gbase + (winm ? (uint32_t)__ffs(winm) - 1u : 0u);
+        best = m;
+        bu = __shfl_sync(FULLM, bu, win); bv = __shfl_sync(FULLM, bv, win);
+        btet = __shfl_sync(FULLM, btet, win); bj = __shfl_sync(FULLM, bj, win);
+    }
+    if (live && btet == TN_EMPTY) { if (lq == 0) p.num[ray] = 0; live = false; }  // the ray misses the mesh
+    if (live && hullhits != 2) {  // origin inside the mesh, or a hull edge / vertex hit: exact all-hits stage (see k_walk)
+        if (lq == 0) {
+            p.list[atomicAdd(p.list_count, 1u)] = ray;
+            atomicAdd(p.list_count + 1, 1u);
+            p.num[ray] = 0;
+        }
+        live = false;
+    }
+
+    // ---- walk: lane lq owns vertex lq / the face opposite to it; every lane of the quad keeps the (quad-uniform) bookkeeping ----
+    uint32_t c = live ? btet : 0u, jin = bj, fin = (uint32_t)best, nfaces = 1, nrec = 0;
+    float t_in = __uint_as_float((uint32_t)(best >> 32)), u_in = bu, v_in = bv;
+    bool generic = true, exact = false, prev_small = false, walking = live;
+    if (live && lq == 0) p.keys[row] = best;
+    while (__any_sync(FULLM, walking)) {
+        const float4 *wp = reinterpret_cast<const float4 *>(p.walk + c);
+        const uint32_t *wq = reinterpret_cast<const uint32_t *>(wp);
+        float4 vj = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t nbj = TN_EMPTY, vidj = 0, wind = 0, perm = 0;
+        if (walking) {
+            vj = __ldg(wp + lq);                  // vertex lq + the face id opposite to it
+            nbj = __ldg(wq + 16 + lq);            // neighbour across my face
+            vidj = __ldg(wq + 20 + lq);           // my vertex id
+            const uint2 wp2 = __ldg(reinterpret_cast<const uint2 *>(wp + 7));
+            wind = wp2.x; perm = wp2.y;
+            if (nbj != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nbj));  // the next record is one of the neighbours
+        }
+        const uint32_t fwj = __float_as_uint(vj.w);
+        const uint32_t inm = (__ballot_sync(FULLM, walking && (fwj & TN_FACE_MASK) == fin) >> gbase) & 0xFu;  // entry face
+        jin = inm ? (uint32_t)__ffs(inm) - 1u : 3u;
+        const Sheared sj = shear(rs, vj.x, vj.y, vj.z);
+        const uint32_t w = (wind >> (6 * lq)) & 63u;  // stored winding of my face as local vertex indices
+        const uint32_t a = gbase + (w & 3u), b = gbase + ((w >> 2) & 3u), cc = gbase + ((w >> 4) & 3u);
+        Sheared A, B, Cv;
+        A.x = __shfl_sync(FULLM, sj.x, a); A.y = __shfl_sync(FULLM, sj.y, a); A.z = __shfl_sync(FULLM, sj.z, a);
+        B.x = __shfl_sync(FULLM, sj.x, b); B.y = __shfl_sync(FULLM, sj.y, b); B.z = __shfl_sync(FULLM, sj.z, b);
+        Cv.x = __shfl_sync(FULLM, sj.x, cc); Cv.y = __shfl_sync(FULLM, sj.y, cc); Cv.z = __shfl_sync(FULLM, sj.z, cc);
+        float t = 0.f, u = 0.f, v = 0.f;
+        const bool hit = walking && lq != jin && tri_test(A, B, Cv, t, u, v);
+        const uint32_t hm = (__ballot_sync(FULLM, hit) >> gbase) & 0xFu;
+        const bool one = __popc(hm) == 1;
+        const uint32_t jout = hm ? (uint32_t)__ffs(hm) - 1u : 0u;
+        const float t_out = __shfl_sync(FULLM, t, gbase + jout), u_out = __shfl_sync(FULLM, u, gbase + jout), v_out = __shfl_sync(FULLM, v, gbase + jout);
+        const uint32_t fout = __shfl_sync(FULLM, fwj, gbase + jout) & TN_FACE_MASK;
+        const uint32_t next = __shfl_sync(FULLM, nbj, gbase + jout);
+        const uint32_t vq = __shfl_sync(FULLM, vidj, gbase + ((perm >> (8 * jin + 2 * lq)) & 3u));
+        if (walking) {
+            if (!one) { exact = true; walking = false; }
+            else {
+                // isolated sub-eps crossings: see k_walk
+                const bool small = fabsf(__fsub_rn(t_out, t_in)) < TN_EPS;
+                if (!(t_out > t_in) || (small && prev_small)) generic = false;
+                prev_small = small;
+                // record (optix_trace_rays.cu:216-225 with combine_indices :39-75): lane q writes slot q of every field
+                if (generic && !small) {
+                    const size_t g = row + nrec;
+                    const uint32_t code = (__ldg(wq + 24 + jin) >> (6 * jout + 2 * lq)) & 3u;  // map[jin]: same line, L1 hit
+                    const float r0 = __fsub_rn(__fsub_rn(1.0f, u_out), v_out), e0 = __fsub_rn(__fsub_rn(1.0f, u_in), v_in);
+                    const float ev = sel3((int)lq, e0, u_in, v_in);
+                    float xv = sel3((int)code, r0, u_out, v_out);
+                    xv = code == 3u ? 0.f : xv;
+                    p.verts[4 * g + lq] = vq;
+                    if (lq < 3u) {
+                        p.bary[6 * g + lq] = ev;
+                        p.bary[6 * g + 3 + lq] = xv;
+                    } else {
+                        p.cells[g] = c;
+                        reinterpret_cast<float2 *>(p.dist)[g] = make_float2(t_in, t_out);
+                    }
+                    nrec++;
+                }
+                if (lq == 0) p.keys[row + nfaces] = ((u64)__float_as_uint(t_out) << 32) | fout;
+                nfaces++;
+                if (next == TN_EMPTY) walking = false;                              // left the mesh
+                else if (nfaces >= p.M - 1) { exact = true; walking = false; }      // truncated by the hit cap: exact stage (see k_walk)
+                else { c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out; }
+            }
+        }
+    }
+    if (!live || lq != 0) return;
+    if (exact) {
+        p.list[atomicAdd(p.list_count, 1u)] = ray;
+        atomicAdd(p.list_count + 1, 1u);  // diagnostics: rays that need the all-hits gather
+        p.num[ray] = 0;
+    } else if (!generic) {
+        p.list[atomicAdd(p.list_count, 1u)] = ray | 0x80000000u;
+        p.num[ray] = nfaces;  // number of keys; the pairing stage replaces it by the number of records
+    } else {
+        p.num[ray] = nrec;
+    }
+}
+
 // dense API tails (optix_trace_rays.cu:260-265 + the zeroed scratch tails pinned by the oracle): one warp per ray
 __global__ void k_tail_fill(uint32_t R, uint32_t M, const uint32_t *__restrict__ num, uint32_t *__restrict__ cells, float *__restrict__ bary,
                             float *__restrict__ dist, uint32_t *__restrict__ verts) {
@@ -380,13 +564,14 @@ __global__ void k_tail_fill(uint32_t R, uint32_t M, const uint32_t *__restrict__
 }
 
 int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32_t M, uint32_t *num, uint32_t *cells, float *bary,
-                float *dist, uint32_t *verts, u64 *keys, uint32_t *list, uint32_t *list_count, bool solo, cudaStream_t s) {
+                float *dist, uint32_t *verts, u64 *keys, uint32_t *list, uint32_t *list_count, int kind, cudaStream_t s) {
     WalkParams p{};
     p.o = o; p.d = d; p.R = R; p.M = M; p.num = num; p.cells = cells; p.bary = bary; p.dist = dist; p.verts = verts;
     p.walk = h->mesh.walk; p.hull_nodes = h->mesh.hull_nodes; p.hull_leaves = h->mesh.hull_leaves; p.hull_tet = h->mesh.hull_tet;
     p.hlv = h->mesh.hull_lv; p.absmax = h->mesh.absmax; p.keys = keys; p.list = list; p.list_count = list_count;
-    if (solo) k_walk_coop<<<R, 32, 0, s>>>(p);
-    else k_walk<<<(R + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(p);
+    if (kind == 1) k_walk_coop<<<R, 32, 0, s>>>(p);                                                           // one ray per warp
+    else if (kind == 2) k_walk_quad<<<(R + QUAD_WARPS * 8 - 1) / (QUAD_WARPS * 8), QUAD_WARPS * 32, 0, s>>>(p);  // 8 rays per warp
+    else k_walk<<<(R + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(p);                             // 32 rays per warp
     h->launches += 1;
     TN_CUDA(cudaGetLastError());
     return TN_OK;

@@ -29,6 +29,7 @@ _lib.tn_render_train_backward.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.POINTER
 _lib.tn_render_debug_buffers.argtypes = [_vp, C.POINTER(_vp)]
 _lib.tn_render_set_profiling.argtypes = [_vp, C.c_int]
 _lib.tn_render_get_timings.argtypes = [_vp, C.POINTER(C.c_float)]
+_lib.tn_render_get_backward_timings.argtypes = [_vp, C.POINTER(C.c_float)]
 KERNEL_NAMES = ["trace", "sample_coarse", "mlp_coarse", "sample_fine", "mlp_fine", "composite"]
 
 PARAM_ORDER = [
@@ -149,6 +150,12 @@ class FusedRenderer:
         arr = (C.c_float * 6)()
         ext._check(_lib.tn_render_get_timings(self.tracer.handle, arr))
         return {n: float(arr[i]) for i, n in enumerate(KERNEL_NAMES)}
+
+    def backward_timings_ms(self) -> Dict[str, float]:
+        """CUDA-event durations of the kernels of the last train_backward() (profiling must be enabled)"""
+        arr = (C.c_float * 3)()
+        ext._check(_lib.tn_render_get_backward_timings(self.tracer.handle, arr))
+        return {n: float(arr[i]) for i, n in enumerate(["composite_bwd", "mlp_bwd", "finalize"])}
 
     def debug_buffers(self):
         arr = (_vp * 16)()

@@ -13,7 +13,7 @@ if len(sys.argv) > 1:
     fr = FusedRenderer(tr); fr.set_field(torch.from_numpy(field).to(dev)); fr.set_weights(bench.mlp_params()); fr.set_profiling(True)
     st = RenderSettings.tetra_nerf()
     res = {}
-    for n in (1024, 4096, 8192, 16384, 65536):
+    for n in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
         o, d = syn.camera_rays(n, seed=3); o, d = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
         for _ in range(2): fr.render(o, d, st)
         t = []
@@ -22,7 +22,7 @@ if len(sys.argv) > 1:
         res[n] = {k: round(float(np.median([x[k] for x in t])), 4) for k in t[0]}
     print(json.dumps(res))
 else:
-    for mode in ("0", "1", "2"):
+    for mode in ("0", "1", "2", "3"):  # BVH gather, walk 32 rays/warp, walk 1 ray/warp, walk 8 rays/warp
         env = dict(os.environ, TETRANERF_B200_WALK=mode)
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         print("WALK=" + mode, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:])
