@@ -103,13 +103,16 @@ struct tn_tracer {
     uint32_t ovf_cap = 0;
     unsigned long long *d_walk_keys = nullptr;  // [R, M] (t, face) keys written by the adjacency walk
     size_t walk_keys_cap = 0;
-    uint32_t walk_min_rays = 10240;  // batches at least this large take the thread-per-ray adjacency walk (see launch_trace)
-    // batches of [walk_solo_min_rays, walk_solo_max_rays] rays (below walk_min_rays) take the one-ray-per-warp walk: measured
-    // (profiles/r1_trace_sweep.json) 0.32 / 0.51 ms at 4096 / 8192 rays against the gather's 0.29 / 0.56 ms
-    uint32_t walk_solo_min_rays = 6144, walk_solo_max_rays = 0xFFFFFFFFu;
-    // batches of [walk_quad_min_rays, walk_quad_max_rays] rays (below walk_min_rays; checked before the solo range) take the walk with
-    // 8 rays per warp, 4 cooperating lanes per ray (default: off until measured; see profiles/r2_trace_sweep.json)
-    uint32_t walk_quad_min_rays = 1, walk_quad_max_rays = 0;
+    // trace_rays picks between bit-identical implementations by batch size (measured on B200, 302k tetrahedra, profiles/r2_trace_sweep.json;
+    // trace time incl. L2 warm-up, ms at 1024 / 4096 / 8192 / 16384 / 65536 rays):
+    //   warp-per-ray all-hits BVH gather   0.19 / 0.31 / 0.57 / 1.02 / 3.51     <- below walk_quad_min_rays
+    //   walk, 8 rays per warp ("quad")     0.30 / 0.31 / 0.32 / 0.45 / 1.56     <- [walk_quad_min_rays, walk_min_rays)
+    //   walk, 1 ray per warp ("solo")      0.26 / 0.35 / 0.55 / 1.00 / 3.57     (kept for tests / experiments: range empty by default)
+    //   walk, 32 rays per warp             0.66 / 0.67 / 0.68 / 0.81 / 1.95     <- >= walk_min_rays (fewest instructions per ray: only pays off
+    //                                                                              once the machine is full several times over)
+    uint32_t walk_min_rays = 1u << 20;
+    uint32_t walk_solo_min_rays = 1, walk_solo_max_rays = 0;
+    uint32_t walk_quad_min_rays = 4608, walk_quad_max_rays = 0xFFFFFFFFu;
     uint64_t launches = 0;
     tn::RenderState *render = nullptr;
 };

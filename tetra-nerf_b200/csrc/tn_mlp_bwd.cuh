@@ -105,19 +105,26 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-// 16 fp32 values (columns col0 .. col0+15 of this thread's row, col0 a multiple of 16) -> bf16 hi/lo, stored into a [row][64-col block]
-// operand buffer (hi at row_addr + block / chunk offsets, lo `lo_off` bytes further).  row_addr = buffer + (R >> 3) * 1024 + (R & 7) * 128.
-__device__ __forceinline__ void store_operand16(uint32_t row_addr, uint32_t r7, uint32_t col0, uint32_t lo_off, const float (&x)[16]) {
+// 16 fp32 values (columns col0 .. col0+15 of this thread's row, col0 a multiple of 16) -> bf16 hi/lo pairs, then stored into a
+// [row][64-col block] operand buffer (hi at row_addr + block / chunk offsets, lo `lo_off` bytes further).
+// row_addr = buffer + (R >> 3) * 1024 + (R & 7) * 128.
+__device__ __forceinline__ void pack16(const float (&x)[16], uint32_t (&h)[8], uint32_t (&l)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tc::split_pack2(x[2 * i], x[2 * i + 1], h[i], l[i]);
+}
+__device__ __forceinline__ void store_packed16(uint32_t row_addr, uint32_t r7, uint32_t col0, uint32_t lo_off, const uint32_t (&h)[8], const uint32_t (&l)[8]) {
     const uint32_t blk = col0 >> 6, c16 = (col0 & 63u) >> 3;  // 16-byte chunk index of the first column inside its 128-byte row
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tc::split_pack2(x[8 * q + 2 * i], x[8 * q + 2 * i + 1], h[i], l[i]);
         const uint32_t a = row_addr + blk * 16384u + (((c16 + (uint32_t)q) ^ r7) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + lo_off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[4 * q]), "r"(h[4 * q + 1]), "r"(h[4 * q + 2]), "r"(h[4 * q + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + lo_off), "r"(l[4 * q]), "r"(l[4 * q + 1]), "r"(l[4 * q + 2]), "r"(l[4 * q + 3]) : "memory");
     }
+}
+__device__ __forceinline__ void store_operand16(uint32_t row_addr, uint32_t r7, uint32_t col0, uint32_t lo_off, const float (&x)[16]) {
+    uint32_t h[8], l[8];
+    pack16(x, h, l);
+    store_packed16(row_addr, r7, col0, lo_off, h, l);
 }
 
 extern __shared__ __align__(1024) uint8_t tn_bwd_smem[];
@@ -543,12 +550,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_mlp_bwd(const MlpBwdParams p
                     ops_arrive(true);
                 }
                 // ---------- E5..E7: dA3, dA2, dA1 = dH * (H > 0); bias gradients ----------
+                // the arithmetic runs as soon as dH is there, under the dW MMAs of the layer above; only the stores wait for them
 #pragma unroll
                 for (int l = 2; l >= 0; --l) {
                     d_wait();
-                    mbar_wait_backoff(&bars[BB_DW_DONE], p_dw, 32);  // the dW MMAs of the layer above have read dA (and H)
-                    p_dw ^= 1u;
                     const unsigned long long mk = mask[l];
+                    uint32_t ph[4][8], pl[4][8];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t col0 = h * 64u + (uint32_t)c * 16u;
@@ -563,9 +570,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_mlp_bwd(const MlpBwdParams p
                             if (l == 2) dh = fmaf(g4.x, wd[col0 + i], dh);  // the density head reads H3 as well
                             x[i] = ((m >> i) & 1u) ? dh : 0.f;
                         }
-                        store_operand16(sDA + rowoff, r7, col0, 32768u, x);
+                        pack16(x, ph[c], pl[c]);
                         acc_b[l][c] += warp_colsum16(x, lane);  // (consumes x)
                     }
+                    mbar_wait_backoff(&bars[BB_DW_DONE], p_dw, 32);  // the dW MMAs of the layer above have read dA (and H)
+                    p_dw ^= 1u;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) store_packed16(sDA + rowoff, r7, h * 64u + (uint32_t)c * 16u, 32768u, ph[c], pl[c]);
                     ops_arrive(true);
                 }
                 // ---------- E8: dX -> field gradient (interpolate_values_backward, tetrahedra_tracer.cu:231-247) ----------

@@ -545,19 +545,35 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_composite_bwd(const Compo
     if (lane == 0) { atomicAdd(p.sums, s0); atomicAdd(p.sums + 1, s1); atomicAdd(p.sums + 2, s2); atomicAdd(p.sums + 3, s3); }
 }
 
-// ---- after k_mlp_bwd: the direction part of mlp_head.layers.0 (W4[:, :27], b4) from the per-ray bias gradients, then all twelve
-// parameter gradients in torch layout.  One block per hidden unit k; lane j < 27 owns W4[k, j], lane 27 the bias.
-__global__ void __launch_bounds__(32) k_dirbias_grads(const uint32_t *__restrict__ n_active, const float *__restrict__ g_dirbias, const float *__restrict__ enc,
-                                                       float *__restrict__ gw) {
-    const uint32_t k = blockIdx.x, lane = threadIdx.x, n = *n_active;
-    float acc = 0.f;
-    for (uint32_t s = 0; s < n; ++s) {
-        const float g = __ldg(g_dirbias + (size_t)s * 128 + k);
-        if (lane < 27) acc = fmaf(g, __ldg(enc + (size_t)s * 27 + lane), acc);
-        else if (lane == 27) acc += g;
+// ---- after k_mlp_bwd: the direction part of mlp_head.layers.0 (W4[:, :27], b4) from the per-ray bias gradients: W4dir[k][j] =
+// sum_slot g_dirbias[slot][k] enc[slot][j], b4[k] = sum_slot g_dirbias[slot][k].  One block per 64 slots, 256 threads: thread t owns
+// hidden unit k = t & 127 and 14 of the 28 columns (27 encoding entries + the bias column of ones); partial sums -> atomicAdd.
+constexpr uint32_t DBG_SLOTS = 64;
+__global__ void __launch_bounds__(256) k_dirbias_grads(const uint32_t *__restrict__ n_active, const float *__restrict__ g_dirbias, const float *__restrict__ enc,
+                                                        float *__restrict__ gw) {
+    __shared__ float s_enc[DBG_SLOTS][28];
+    const uint32_t n = *n_active, s0 = blockIdx.x * DBG_SLOTS;
+    if (s0 >= n) return;
+    const uint32_t ns = min(DBG_SLOTS, n - s0);
+    for (uint32_t i = threadIdx.x; i < ns * 28; i += 256) {
+        const uint32_t s = i / 28, j = i % 28;
+        s_enc[s][j] = j < 27 ? __ldg(enc + (size_t)(s0 + s) * 27 + j) : 1.0f;
     }
-    if (lane < 27) gw[GW_W4DIR + k * 27 + lane] = acc;
-    else if (lane == 27) gw[GW_B4 + k] = acc;
+    __syncthreads();
+    const uint32_t k = threadIdx.x & 127u, j0 = (threadIdx.x >> 7) * 14u;
+    float acc[14];
+#pragma unroll
+    for (int j = 0; j < 14; ++j) acc[j] = 0.f;
+    for (uint32_t s = 0; s < ns; ++s) {
+        const float g = __ldg(g_dirbias + (size_t)(s0 + s) * 128 + k);
+#pragma unroll
+        for (int j = 0; j < 14; ++j) acc[j] = fmaf(g, s_enc[s][j0 + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 14; ++j) {
+        const uint32_t col = j0 + (uint32_t)j;
+        atomicAdd(col < 27 ? gw + GW_W4DIR + k * 27 + col : gw + GW_B4 + k, acc[j]);
+    }
 }
 struct GradOut { float *p[12]; };
 __global__ void k_scatter_grads(const float *__restrict__ gw, const GradOut o) {
@@ -832,7 +848,7 @@ extern "C" int tn_render_train_backward(tn_tracer *h, const float *d_grad_rgb, c
     const uint32_t tiles = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
     k_mlp_bwd<<<std::min<uint32_t>(tiles, (uint32_t)sms), BWD_THREADS, BWD_SMEM_BYTES, s>>>(bp);
     if (r->profile) cudaEventRecord(r->evb[2], s);
-    k_dirbias_grads<<<128, 32, 0, s>>>(r->n_active, r->g_dirbias, r->enc, r->gw);
+    k_dirbias_grads<<<(R + DBG_SLOTS - 1) / DBG_SLOTS, 256, 0, s>>>(r->n_active, r->g_dirbias, r->enc, r->gw);
     GradOut go{};
     for (int i = 0; i < 12; ++i) {
         if (!d_grad_params12[i]) return fail(TN_ERR_ARG, "tn_render_train_backward: null parameter gradient pointer");
