@@ -107,13 +107,19 @@ __device__ __forceinline__ void split2(float2 r, uint32_t &hi, uint32_t &lo) {
 }
 
 // epilogue of one layer for one warp: its 32 rows x 64 columns [64h, 64h+64) of the accumulator.
-//   KIND 0: hidden layer  -> bias + ReLU, next A operand
-//   KIND 1: 3rd layer     -> as 0, plus the density-head partial dot product (acc.x)
+//   KIND 0: hidden layer  -> bias + ReLU, next A operand; with `dens` (3rd layer of the FINE pass) also the density-head partial dot
+//           product (acc.x)
 //   KIND 2: 3rd layer, last (COARSE) -> bias + ReLU + density partial, no next operand
 //   KIND 3: 4th layer (FINE, last)   -> per-ray bias + ReLU + colour-head partial (acc.y/z/w)
+// (one body per KIND and a NON-unrolled layer loop around them: the 16 worker warps of the two slots run different layers at the same
+//  time, and with one copy of this code per layer the epilogues did not fit the 32 KB instruction cache -- ncu: 15 % of all stall
+//  samples "no instruction".)
+// The bias of the first 16 columns is loaded by the caller BEFORE it waits for the accumulator (bpre), and every bias register is
+// refilled with the next chunk's value as soon as it has been consumed: the loads (L1 / L2, SM-dependent latency) never sit between
+// the TMEM load and the first add any more.
 template <int KIND>
-__device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint32_t alo, uint32_t h, const float *__restrict__ bias128,
-                                               const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc) {
+__device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint32_t alo, uint32_t h, const float *__restrict__ bias128, float2 (&bpre)[8],
+                                               bool dens, const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc) {
     using namespace tc;
     float2 dsum = make_float2(0.f, 0.f), c0 = dsum, c1 = dsum, c2 = dsum;
     // 4 chunks of 16 accumulator columns (small register footprint); the TMEM load of chunk ch+1 is in flight while
@@ -129,25 +135,31 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
         uint32_t ph[8], pl[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float2 b = __ldg(reinterpret_cast<const float2 *>(bias128 + col0 + 2 * i));  // global, L1-resident
+            const float2 b = bpre[i];
+            if (ch + 1 < 4) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + col0 + 16u + 2 * i));  // next chunk's bias, a chunk ahead
             float2 x = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b);
             x.x = fmaxf(x.x, 0.f);
             x.y = fmaxf(x.y, 0.f);
-            if (KIND == 0 || KIND == 1) split2(x, ph[i], pl[i]);
-            if (KIND == 1 || KIND == 2) dsum = fma2(x, *reinterpret_cast<const float2 *>(wd + col0 + 2 * i), dsum);
+            if (KIND == 0) split2(x, ph[i], pl[i]);
+            if (KIND == 2 || (KIND == 0 && dens)) dsum = fma2(x, *reinterpret_cast<const float2 *>(wd + col0 + 2 * i), dsum);
             if (KIND == 3) {
                 c0 = fma2(x, *reinterpret_cast<const float2 *>(wc + col0 + 2 * i), c0);
                 c1 = fma2(x, *reinterpret_cast<const float2 *>(wc + 128 + col0 + 2 * i), c1);
                 c2 = fma2(x, *reinterpret_cast<const float2 *>(wc + 256 + col0 + 2 * i), c2);
             }
         }
-        if (KIND == 0 || KIND == 1) {
+        if (KIND == 0) {
             tmem_st8(ahi + (col0 >> 1), ph);
             tmem_st8(alo + (col0 >> 1), pl);
         }
     }
-    if (KIND == 1 || KIND == 2) acc.x = dsum.x + dsum.y;
+    if (KIND == 2 || (KIND == 0 && dens)) acc.x = dsum.x + dsum.y;
     if (KIND == 3) { acc.y = c0.x + c0.y; acc.z = c1.x + c1.y; acc.w = c2.x + c2.y; }
+}
+// the first chunk's bias of a layer (16 columns from 64 h): issued before the wait for that layer's accumulator
+__device__ __forceinline__ void bias_prefetch(const float *__restrict__ bias128, uint32_t h, float2 (&bpre)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + h * 64u + 2 * i));
 }
 
 extern __shared__ __align__(1024) uint8_t tn_mlp_smem[];
@@ -541,7 +553,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
             uint64_t my_row = 0;
             const float *bias4 = nullptr;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+            float2 bpre[8];
+            bias_prefetch(p.bias, h, bpre);  // layer 0: known before the tile is
+#pragma unroll 1
             for (int l = 0; l < L; ++l) {
                 tl_mark(p.timeline, lane, warp, 7, n, l);  // ev 7: start waiting for D
                 mbar_wait_backoff(&d_ready[slot], dpar, 32);
@@ -553,15 +567,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
                     if (tile == MLP_NO_TILE) break;  // retired by the issuer
                     ++ntl;
                     my_row = (uint64_t)tile * 128u + q * 32u + (uint32_t)lane;
-                    if (FINE) {  // per-ray direction bias of this thread's row (read through L1 in the last epilogue; warm the line now)
-                        bias4 = p.dirbias + (size_t)(min(my_row, total_rows - 1) / p.S) * 128;
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(bias4 + ((uint32_t)lane & 3u) * 32u));
-                    }
+                    if (FINE) bias4 = p.dirbias + (size_t)(min(my_row, total_rows - 1) / p.S) * 128;  // per-ray direction bias of this thread's row
                 }
-                if (l < 2) layer_epilogue<0>(d_t, ahi, alo, h, p.bias + l * 128, wd, wc, acc);
-                else if (l == 2 && FINE) layer_epilogue<1>(d_t, ahi, alo, h, p.bias + 256, wd, wc, acc);
-                else if (l == 2) layer_epilogue<2>(d_t, ahi, alo, h, p.bias + 256, wd, wc, acc);
-                else layer_epilogue<3>(d_t, ahi, alo, h, bias4, wd, wc, acc);
+                if (l < L - 1) {
+                    layer_epilogue<0>(d_t, ahi, alo, h, p.bias + l * 128, bpre, FINE && l == 2, wd, wc, acc);
+                    // the next layer's first bias chunk: in flight while the next GEMM runs
+                    if (FINE && l == 2) bias_prefetch(bias4, h, bpre); else bias_prefetch(p.bias + (l + 1) * 128, h, bpre);
+                } else if (FINE) {
+                    layer_epilogue<3>(d_t, ahi, alo, h, bias4, bpre, false, wd, wc, acc);
+                } else {
+                    layer_epilogue<2>(d_t, ahi, alo, h, p.bias + 256, bpre, false, wd, wc, acc);
+                }
                 // next A operand written (l < L-1) / accumulator read out and free for the next tile (l == L-1)
                 if (l < L - 1) tmem_st_wait();
                 fence_before_sync();

@@ -459,6 +459,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_mlp_bwd(const MlpBwdParams p
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BB_OPS_READY]);
         };
+        float bq[16];  // bias of the chunk that is processed next (loaded a chunk ahead: never between the TMEM load and its use)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bq[i] = __ldg(p.bias + h * 64u + i);
         if (has_work) {
             for (uint32_t n = 0;; ++n) {
                 d_wait();  // forward layer 1 of the CTA's n-th tile (or the issuer's wake-up call when there is none)
@@ -485,7 +488,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_mlp_bwd(const MlpBwdParams p
                         uint32_t m = 0;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float v = __uint_as_float(r[i]) + __ldg(bias + col0 + i);
+                            const float v = __uint_as_float(r[i]) + bq[i];
+                            // refill with the bias of the next chunk / the next layer's first chunk: a chunk ahead of its use
+                            if (c < 3) bq[i] = __ldg(bias + col0 + 16u + i);
+                            else bq[i] = __ldg(p.bias + (l < 2 ? (l + 1) * 128 : 0) + h * 64u + i);  // (after layer 3: layer 1 of the next tile)
                             m |= (v > 0.f ? 1u : 0u) << i;
                             x[i] = fmaxf(v, 0.f);
                         }
