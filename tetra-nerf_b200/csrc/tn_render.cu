@@ -689,6 +689,7 @@ static int render_impl(tn_tracer *h, const tn_render_config *cfg, const float *d
     if (Sc == 0 || Sc > 4096 || Sf > 4096) return fail(TN_ERR_ARG, "tn_render: num_samples must be in [1,4096]");
     if (tf != nullptr && Sf == 0) return fail(TN_ERR_ARG, "tn_render_train_forward: the fused training step needs num_fine_samples > 0");
     if (R == 0) return TN_OK;
+    if ((uint64_t)R * (uint64_t)(Sc + Sf + 1) >= (1ull << 32)) return fail(TN_ERR_ARG, "tn_render: rays x samples must stay below 2^32 per call (split the batch)");
     const bool single = Sf == 0;                       // one pass only: the colours come from the coarse samples
     const uint32_t S2 = single ? Sc : Sc + Sf + 1;     // PDFSampler include_original (model.py:463)
     DeviceGuard g(h->device);
