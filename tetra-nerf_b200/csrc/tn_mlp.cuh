@@ -50,7 +50,7 @@ constexpr uint32_t MLP_OFF_RING = MLP_W_RESIDENT;                               
 constexpr uint32_t MLP_OFF_A0 = MLP_OFF_RING + MLP_RING_STAGES * MLP_RING_CHUNK; // layer-0 A operand: hi 16K | lo 16K
 constexpr uint32_t MLP_OFF_HEAD = MLP_OFF_A0 + 32768;                            // wd[128] wc[3][128] bd bc[3] (+pad)
 constexpr uint32_t MLP_OFF_BARS = MLP_OFF_HEAD + 520 * 4;
-constexpr uint32_t MLP_OFF_TL = MLP_OFF_BARS + 144;  // debug timeline: counter, enable flag, MLP_TL_CAP records
+constexpr uint32_t MLP_OFF_TL = MLP_OFF_BARS + 160;  // debug timeline: counter, enable flag, MLP_TL_CAP records
 // (the hidden-layer biases are read through L1 and the head partial sums are exchanged through TMEM: with 160 KB of
 //  resident weights, the 32 KB ring and the 32 KB layer-0 operand there is no shared memory left for them)
 constexpr uint32_t MLP_SMEM_BYTES = MLP_OFF_TL + 8 * (MLP_TL_CAP + 2);
@@ -119,24 +119,28 @@ __device__ __forceinline__ void split2(float2 r, uint32_t &hi, uint32_t &lo) {
 // the TMEM load and the first add any more.
 template <int KIND>
 __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint32_t alo, uint32_t cq, const float *__restrict__ bias128, float2 (&bpre)[8],
-                                               bool dens, const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc) {
+                                               bool dens, const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc, uint64_t *bar_k0,
+                                               uint64_t *bar_k1, int lane) {
     using namespace tc;
     float2 dsum = make_float2(0.f, 0.f), c0 = dsum, c1 = dsum, c2 = dsum;
-    // this warp's 32 accumulator columns [32 cq, 32 cq + 32) in 2 chunks of 16; the TMEM load of the second chunk is in flight while
-    // the first is processed
+    // this warp's 2 x 16 accumulator columns: [16 cq, +16) of the first 64-wide K block of the next layer and [64 + 16 cq, +16) of the
+    // second.  Both chunks are in registers before the first arrival, so the next GEMM may overwrite the accumulator from then on:
+    // its K-block-0 MMAs run while the second chunk is still being processed.
     uint32_t rbuf[2][16];
-    tmem_ld16(d_t + cq * 32u, rbuf[0]);
+    tmem_ld16(d_t + cq * 16u, rbuf[0]);
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-        const uint32_t col0 = cq * 32u + ch * 16u;
-        tmem_ld_wait();
-        if (ch + 1 < 2) tmem_ld16(d_t + col0 + 16u, rbuf[(ch + 1) & 1]);
+        const uint32_t col0 = (uint32_t)ch * 64u + cq * 16u;
+        if (ch == 0) {
+            tmem_ld_wait();
+            tmem_ld16(d_t + 64u + cq * 16u, rbuf[1]);
+        }
         const uint32_t *r = rbuf[ch & 1];
         uint32_t ph[8], pl[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float2 b = bpre[i];
-            if (ch + 1 < 2) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + col0 + 16u + 2 * i));  // next chunk's bias, a chunk ahead
+            if (ch == 0) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + 64u + cq * 16u + 2 * i));  // second chunk's bias, a chunk ahead
             float2 x = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b);
             x.x = fmaxf(x.x, 0.f);
             x.y = fmaxf(x.y, 0.f);
@@ -152,14 +156,19 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
             tmem_st8(ahi + (col0 >> 1), ph);
             tmem_st8(alo + (col0 >> 1), pl);
         }
+        if (ch == 0) tmem_ld_wait();  // the second chunk has left the accumulator as well
+        if (KIND == 0) tmem_st_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ch == 0 ? bar_k0 : bar_k1);
     }
     if (KIND == 2 || (KIND == 0 && dens)) acc.x = dsum.x + dsum.y;
     if (KIND == 3) { acc.y = c0.x + c0.y; acc.z = c1.x + c1.y; acc.w = c2.x + c2.y; }
 }
-// the first chunk's bias of a layer (16 columns from 32 cq): issued before the wait for that layer's accumulator
+// the first chunk's bias of a layer (16 columns from 16 cq): issued before the wait for that layer's accumulator
 __device__ __forceinline__ void bias_prefetch(const float *__restrict__ bias128, uint32_t cq, float2 (&bpre)[8]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + cq * 32u + 2 * i));
+    for (int i = 0; i < 8; ++i) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + cq * 16u + 2 * i));
 }
 
 extern __shared__ __align__(1024) uint8_t tn_mlp_smem[];
@@ -193,7 +202,7 @@ struct MlpIssue {
     uint32_t nseq, done;   // sequence number of the CTA's next tile; set once the tile scheduler has run dry
 };
 constexpr uint32_t MLP_BAR_A_READY = 0, MLP_BAR_D_READY = 2, MLP_BAR_W = 4, MLP_BAR_RING_FULL = 5, MLP_BAR_RING_EMPTY = 7, MLP_BAR_A0_FULL = 9,
-                   MLP_BAR_A0_EMPTY = 11;
+                   MLP_BAR_A0_EMPTY = 11, MLP_BAR_A_READY2 = 18;  // (bytes 104..143 of the block: TMEM pointer, stop flag, tile_ids)
 constexpr uint32_t MLP_TILE_IDS_OFF = 112;        // byte offset of tile_ids[8] inside the barrier block (after 13 barriers + tmem ptr + stop flag)
 constexpr uint32_t MLP_NO_TILE = 0xFFFFFFFFu;     // sentinel: the scheduler has run dry
 
@@ -240,7 +249,10 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
     constexpr uint32_t L = FINE ? 4 : 3;
     constexpr uint32_t NBUF = FINE ? 1 : 2;
     constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    // the workers arrive twice per layer: K block 0 of the next A operand written and the whole accumulator read out (A_READY), then
+    // K block 1 written (A_READY2).  The MMAs of K block 0 are issued in between.
     mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY + SLOT), par);
+    const uint32_t par2 = par;
     par ^= 1u;
     const uint32_t l = layer;
     layer = l + 1u == L ? 0u : l + 1u;
@@ -250,6 +262,7 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         // gather warps (hi block, lo block 16 KB further); resident image: L1 hi at 0, lo at 16 KB
         uint32_t tile = MLP_NO_TILE;
         const uint32_t b = NBUF == 2 ? (s.nseq & 1u) : 0u;
+        mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY2 + SLOT), par2);
         if (!s.done) {
             mbar_wait_a(s.bars + 8u * (MLP_BAR_A0_FULL + b), (s.nseq / NBUF) & 1u);
             asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tile) : "r"(s.bars + MLP_TILE_IDS_OFF + 4u * (s.nseq & 7u)) : "memory");
@@ -281,9 +294,13 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         tl_mark(p.timeline, 0, 17, 1 + SLOT, 0, l);
         if (l == 1) {
             kblock_ts<true, 0u, 2048u, 3072u>(d_t, a, s.dw, idesc);
+            mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY2 + SLOT), par2);
+            fence_after_sync();
             kblock_ts<false, 1u, 4096u, 5120u>(d_t, a, s.dw, idesc);
         } else if (l == 2) {
             kblock_ts<true, 0u, 6144u, 7168u>(d_t, a, s.dw, idesc);
+            mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY2 + SLOT), par2);
+            fence_after_sync();
             kblock_ts<false, 1u, 8192u, 9216u>(d_t, a, s.dw, idesc);
         } else {
             // layer 4: the chunks hi(kb0) lo(kb0) hi(kb1) lo(kb1) stream through the ring
@@ -294,7 +311,10 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         mma_commit_a(s.bars + 8u * (MLP_BAR_RING_EMPTY + s.rst));                                     \
         if (++s.rst == MLP_RING_STAGES) { s.rst = 0; s.rpar ^= 1u; }                                  \
     }
-            TN_RING_CHUNK(0) TN_RING_CHUNK(1) TN_RING_CHUNK(2) TN_RING_CHUNK(3)
+            TN_RING_CHUNK(0) TN_RING_CHUNK(1)
+            mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY2 + SLOT), par2);
+            fence_after_sync();
+            TN_RING_CHUNK(2) TN_RING_CHUNK(3)
 #undef TN_RING_CHUNK
         }
     }
@@ -335,6 +355,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
     if (warp == 16) {
         if (lane == 0) {
             mbar_init(&a_ready[0], 16); mbar_init(&a_ready[1], 16);
+            mbar_init(&bars[MLP_BAR_A_READY2], 16); mbar_init(&bars[MLP_BAR_A_READY2 + 1], 16);
             mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
             mbar_init(w_bar, 1);
             for (int i = 0; i < 2; ++i) {
@@ -572,15 +593,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
             }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (l < (uint32_t)(L - 1)) {
-                layer_epilogue<0>(d_t, ahi, alo, cq, bl, bpre, FINE && l == 2u, wd, wc, acc);
+                layer_epilogue<0>(d_t, ahi, alo, cq, bl, bpre, FINE && l == 2u, wd, wc, acc, &a_ready[slot], &bars[MLP_BAR_A_READY2 + slot], lane);
                 if (FINE && l == 2u) dens = acc.x;
-                tmem_st_wait();  // the next A operand is written
             } else if (FINE) {
-                layer_epilogue<3>(d_t, ahi, alo, cq, bl, bpre, false, wd, wc, acc);
+                layer_epilogue<3>(d_t, ahi, alo, cq, bl, bpre, false, wd, wc, acc, &a_ready[slot], &bars[MLP_BAR_A_READY2 + slot], lane);
                 acc.x = dens;
             } else {
-                layer_epilogue<2>(d_t, ahi, alo, cq, bl, bpre, false, wd, wc, acc);
+                layer_epilogue<2>(d_t, ahi, alo, cq, bl, bpre, false, wd, wc, acc, &a_ready[slot], &bars[MLP_BAR_A_READY2 + slot], lane);
             }
+            // (both arrivals of this layer have been made inside: the slot is back with the issuer)
             if (l == (uint32_t)(L - 1)) {
                 // ---- heads: combine the four column quarters, activation, store ----
                 // The partial sums of quarters 1..3 travel through TMEM: the first twelve columns of the slot's A region (dead once the
@@ -610,18 +631,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
                     }
                 }
             }
-            // the accumulator has been read out (and, for a hidden layer, the next A operand written): hand the slot back to the issuer
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[slot]);
-            tl_mark(p.timeline, lane, warp, 9, n, l);  // ev 9: epilogue of layer l done (+arrive)
+            tl_mark(p.timeline, lane, warp, 9, n, l);  // ev 9: epilogue of layer l done
             const uint32_t nl = l + 1u == (uint32_t)L ? 0u : l + 1u, nn = nl == 0u ? n + 2u : n;
             pk = nl | ((par ^ 1u) << 3) | (nn << 4);
             if (slot) { pk1 = pk; row1 = row; dens1 = dens; } else { pk0 = pk; row0 = row; dens0 = dens; }
             return true;
         };
         if (has_work) {
-            if (lane == 0) { mbar_arrive(&a_ready[0]); mbar_arrive(&a_ready[1]); }  // both accumulators are free for the first tiles
+            if (lane == 0) {  // both accumulators are free for the first tiles
+                mbar_arrive(&a_ready[0]); mbar_arrive(&a_ready[1]);
+                mbar_arrive(&bars[MLP_BAR_A_READY2]); mbar_arrive(&bars[MLP_BAR_A_READY2 + 1]);
+            }
             // the issuer's order: slot 0 once, then strictly alternating, each slot until it is retired
             bool alive0 = step(0u), alive1 = true;
             while (alive0 | alive1) {
