@@ -50,7 +50,7 @@ constexpr uint32_t MLP_OFF_RING = MLP_W_RESIDENT;                               
 constexpr uint32_t MLP_OFF_A0 = MLP_OFF_RING + MLP_RING_STAGES * MLP_RING_CHUNK; // layer-0 A operand: hi 16K | lo 16K
 constexpr uint32_t MLP_OFF_HEAD = MLP_OFF_A0 + 32768;                            // wd[128] wc[3][128] bd bc[3] (+pad)
 constexpr uint32_t MLP_OFF_BARS = MLP_OFF_HEAD + 520 * 4;
-constexpr uint32_t MLP_OFF_TL = MLP_OFF_BARS + 160;  // debug timeline: counter, enable flag, MLP_TL_CAP records
+constexpr uint32_t MLP_OFF_TL = MLP_OFF_BARS + 144;  // debug timeline: counter, enable flag, MLP_TL_CAP records
 // (the hidden-layer biases are read through L1 and the head partial sums are exchanged through TMEM: with 160 KB of
 //  resident weights, the 32 KB ring and the 32 KB layer-0 operand there is no shared memory left for them)
 constexpr uint32_t MLP_SMEM_BYTES = MLP_OFF_TL + 8 * (MLP_TL_CAP + 2);
@@ -118,29 +118,25 @@ __device__ __forceinline__ void split2(float2 r, uint32_t &hi, uint32_t &lo) {
 // refilled with the next chunk's value as soon as it has been consumed: the loads (L1 / L2, SM-dependent latency) never sit between
 // the TMEM load and the first add any more.
 template <int KIND>
-__device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint32_t alo, uint32_t cq, const float *__restrict__ bias128, float2 (&bpre)[8],
-                                               bool dens, const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc, uint64_t *bar_k0,
-                                               uint64_t *bar_k1, int lane) {
+__device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint32_t alo, uint32_t h, const float *__restrict__ bias128, float2 (&bpre)[8],
+                                               bool dens, const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc) {
     using namespace tc;
     float2 dsum = make_float2(0.f, 0.f), c0 = dsum, c1 = dsum, c2 = dsum;
-    // this warp's 2 x 16 accumulator columns: [16 cq, +16) of the first 64-wide K block of the next layer and [64 + 16 cq, +16) of the
-    // second.  Both chunks are in registers before the first arrival, so the next GEMM may overwrite the accumulator from then on:
-    // its K-block-0 MMAs run while the second chunk is still being processed.
+    // 4 chunks of 16 accumulator columns (small register footprint); the TMEM load of chunk ch+1 is in flight while
+    // chunk ch is processed
     uint32_t rbuf[2][16];
-    tmem_ld16(d_t + cq * 16u, rbuf[0]);
+    tmem_ld16(d_t + h * 64u, rbuf[0]);
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-        const uint32_t col0 = (uint32_t)ch * 64u + cq * 16u;
-        if (ch == 0) {
-            tmem_ld_wait();
-            tmem_ld16(d_t + 64u + cq * 16u, rbuf[1]);
-        }
+    for (int ch = 0; ch < 4; ++ch) {
+        const uint32_t col0 = h * 64u + ch * 16u;
+        tmem_ld_wait();
+        if (ch + 1 < 4) tmem_ld16(d_t + col0 + 16u, rbuf[(ch + 1) & 1]);
         const uint32_t *r = rbuf[ch & 1];
         uint32_t ph[8], pl[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float2 b = bpre[i];
-            if (ch == 0) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + 64u + cq * 16u + 2 * i));  // second chunk's bias, a chunk ahead
+            if (ch + 1 < 4) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + col0 + 16u + 2 * i));  // next chunk's bias, a chunk ahead
             float2 x = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b);
             x.x = fmaxf(x.x, 0.f);
             x.y = fmaxf(x.y, 0.f);
@@ -156,19 +152,14 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
             tmem_st8(ahi + (col0 >> 1), ph);
             tmem_st8(alo + (col0 >> 1), pl);
         }
-        if (ch == 0) tmem_ld_wait();  // the second chunk has left the accumulator as well
-        if (KIND == 0) tmem_st_wait();
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ch == 0 ? bar_k0 : bar_k1);
     }
     if (KIND == 2 || (KIND == 0 && dens)) acc.x = dsum.x + dsum.y;
     if (KIND == 3) { acc.y = c0.x + c0.y; acc.z = c1.x + c1.y; acc.w = c2.x + c2.y; }
 }
-// the first chunk's bias of a layer (16 columns from 16 cq): issued before the wait for that layer's accumulator
-__device__ __forceinline__ void bias_prefetch(const float *__restrict__ bias128, uint32_t cq, float2 (&bpre)[8]) {
+// the first chunk's bias of a layer (16 columns from 64 h): issued before the wait for that layer's accumulator
+__device__ __forceinline__ void bias_prefetch(const float *__restrict__ bias128, uint32_t h, float2 (&bpre)[8]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + cq * 16u + 2 * i));
+    for (int i = 0; i < 8; ++i) bpre[i] = __ldg(reinterpret_cast<const float2 *>(bias128 + h * 64u + 2 * i));
 }
 
 extern __shared__ __align__(1024) uint8_t tn_mlp_smem[];
@@ -202,7 +193,7 @@ struct MlpIssue {
     uint32_t nseq, done;   // sequence number of the CTA's next tile; set once the tile scheduler has run dry
 };
 constexpr uint32_t MLP_BAR_A_READY = 0, MLP_BAR_D_READY = 2, MLP_BAR_W = 4, MLP_BAR_RING_FULL = 5, MLP_BAR_RING_EMPTY = 7, MLP_BAR_A0_FULL = 9,
-                   MLP_BAR_A0_EMPTY = 11, MLP_BAR_A_READY2 = 18;  // (bytes 104..143 of the block: TMEM pointer, stop flag, tile_ids)
+                   MLP_BAR_A0_EMPTY = 11;
 constexpr uint32_t MLP_TILE_IDS_OFF = 112;        // byte offset of tile_ids[8] inside the barrier block (after 13 barriers + tmem ptr + stop flag)
 constexpr uint32_t MLP_NO_TILE = 0xFFFFFFFFu;     // sentinel: the scheduler has run dry
 
@@ -249,10 +240,7 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
     constexpr uint32_t L = FINE ? 4 : 3;
     constexpr uint32_t NBUF = FINE ? 1 : 2;
     constexpr uint32_t idesc = make_idesc_bf16(128, 128);
-    // the workers arrive twice per layer: K block 0 of the next A operand written and the whole accumulator read out (A_READY), then
-    // K block 1 written (A_READY2).  The MMAs of K block 0 are issued in between.
     mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY + SLOT), par);
-    const uint32_t par2 = par;
     par ^= 1u;
     const uint32_t l = layer;
     layer = l + 1u == L ? 0u : l + 1u;
@@ -262,7 +250,6 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         // gather warps (hi block, lo block 16 KB further); resident image: L1 hi at 0, lo at 16 KB
         uint32_t tile = MLP_NO_TILE;
         const uint32_t b = NBUF == 2 ? (s.nseq & 1u) : 0u;
-        mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY2 + SLOT), par2);
         if (!s.done) {
             mbar_wait_a(s.bars + 8u * (MLP_BAR_A0_FULL + b), (s.nseq / NBUF) & 1u);
             asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tile) : "r"(s.bars + MLP_TILE_IDS_OFF + 4u * (s.nseq & 7u)) : "memory");
@@ -294,13 +281,9 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         tl_mark(p.timeline, 0, 17, 1 + SLOT, 0, l);
         if (l == 1) {
             kblock_ts<true, 0u, 2048u, 3072u>(d_t, a, s.dw, idesc);
-            mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY2 + SLOT), par2);
-            fence_after_sync();
             kblock_ts<false, 1u, 4096u, 5120u>(d_t, a, s.dw, idesc);
         } else if (l == 2) {
             kblock_ts<true, 0u, 6144u, 7168u>(d_t, a, s.dw, idesc);
-            mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY2 + SLOT), par2);
-            fence_after_sync();
             kblock_ts<false, 1u, 8192u, 9216u>(d_t, a, s.dw, idesc);
         } else {
             // layer 4: the chunks hi(kb0) lo(kb0) hi(kb1) lo(kb1) stream through the ring
@@ -311,10 +294,7 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         mma_commit_a(s.bars + 8u * (MLP_BAR_RING_EMPTY + s.rst));                                     \
         if (++s.rst == MLP_RING_STAGES) { s.rst = 0; s.rpar ^= 1u; }                                  \
     }
-            TN_RING_CHUNK(0) TN_RING_CHUNK(1)
-            mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY2 + SLOT), par2);
-            fence_after_sync();
-            TN_RING_CHUNK(2) TN_RING_CHUNK(3)
+            TN_RING_CHUNK(0) TN_RING_CHUNK(1) TN_RING_CHUNK(2) TN_RING_CHUNK(3)
 #undef TN_RING_CHUNK
         }
     }
@@ -331,7 +311,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
     uint8_t *ring_s = smem + MLP_OFF_RING;
     float *head_s = reinterpret_cast<float *>(smem + MLP_OFF_HEAD);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + MLP_OFF_BARS);
-    uint64_t *a_ready = bars + MLP_BAR_A_READY;        // [2] count 16: the worker warps are done with the slot's D / have written its next A
+    uint64_t *a_ready = bars + MLP_BAR_A_READY;        // [2] count 8: the slot's warps are done with D / have written the next A
     uint64_t *d_ready = bars + MLP_BAR_D_READY;        // [2] count 1 (tcgen05.commit; plain arrive when the slot is retired)
     uint64_t *w_bar = bars + MLP_BAR_W;                // resident weights landed
     uint64_t *ring_full = bars + MLP_BAR_RING_FULL;    // [2]
@@ -354,8 +334,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
 
     if (warp == 16) {
         if (lane == 0) {
-            mbar_init(&a_ready[0], 16); mbar_init(&a_ready[1], 16);
-            mbar_init(&bars[MLP_BAR_A_READY2], 16); mbar_init(&bars[MLP_BAR_A_READY2 + 1], 16);
+            mbar_init(&a_ready[0], 8); mbar_init(&a_ready[1], 8);
             mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
             mbar_init(w_bar, 1);
             for (int i = 0; i < 2; ++i) {
@@ -558,96 +537,81 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
 #undef TN_LOAD_IDS
         }
     } else {
-        // ================= worker warps: the per-layer epilogues and heads of BOTH slots =================
-        // The issuer alternates strictly between the slots, so their epilogues never run at the same time: all 16 worker warps serve
-        // whichever slot's accumulator is ready (32 rows x 32 columns each: warp = (TMEM lane quarter q, column quarter cq)).  An
-        // epilogue then takes half as long as with 8 warps per slot and fits under the other slot's GEMM, which is what keeps the
-        // tensor pipe fed (with 8 + 8 warps the issuer waited ~1.3k cycles per layer for the epilogue chain, profiles/README.md).
+        // ================= slot warps: per-layer epilogues, heads =================
         reg_inc<MLP_REGS_WORKER>();
-        const uint32_t cq = (uint32_t)warp >> 2;  // column quarter
-        const uint32_t q = (uint32_t)warp & 3u;   // TMEM lane quarter this warp may access
+        const int slot = warp >> 3;
+        const uint32_t h = (uint32_t)(warp >> 2) & 1u;  // column half
+        const uint32_t q = (uint32_t)warp & 3u;         // TMEM lane quarter this warp may access
         const uint32_t lane_base = (q * 32u) << 16;
+        const uint32_t d_t = tbase + 256u * slot + lane_base, ahi = d_t + 128u, alo = d_t + 192u;
         const float *wd = head_s, *wc = head_s + 128;
-        uint32_t ntl = 0;
-        // per-slot state, kept in registers (selected by the warp-uniform slot): pk = layer | phase << 3 | tile sequence number << 4
-        uint32_t pk0 = 0u << 4, pk1 = 1u << 4, row0 = 0, row1 = 0;
-        float dens0 = 0.f, dens1 = 0.f;
-        auto step = [&](const uint32_t slot) -> bool {  // one layer of one slot; false once the slot has been retired by the issuer
-            uint32_t pk = slot ? pk1 : pk0, row = slot ? row1 : row0;
-            float dens = slot ? dens1 : dens0;
-            const uint32_t l = pk & 7u, par = (pk >> 3) & 1u, n = pk >> 4;
-            const uint32_t d_t = tbase + 256u * slot + lane_base, ahi = d_t + 128u, alo = d_t + 192u;
-            // this layer's first bias chunk, issued before the wait (layer 4 of the FINE pass: the per-ray direction bias of this row)
-            const float *bl = (FINE && l == 3u) ? p.dirbias + (size_t)(min((uint64_t)row, total_rows - 1) / p.S) * 128 : p.bias + l * 128u;
-            float2 bpre[8];
-            bias_prefetch(bl, cq, bpre);
-            tl_mark(p.timeline, lane, warp, 7, n, l);  // ev 7: start waiting for D
-            mbar_wait_backoff(&d_ready[slot], par, 32);
-            fence_after_sync();
-            tl_mark(p.timeline, lane, warp, 8, n, l);  // ev 8: D ready seen
-            if (l == 0u) {
-                const uint32_t tile = tile_ids[n & 7u];
-                if (tile == MLP_NO_TILE) return false;  // retired by the issuer
-                ++ntl;
-                row = tile * 128u + q * 32u + (uint32_t)lane;
-            }
+        uint32_t dpar = 0, ntl = 0;
+        if (has_work) {
+        if (lane == 0) mbar_arrive(&a_ready[slot]);  // the slot's accumulator is free for the first tile
+        for (uint32_t n = slot;; n += 2) {            // the slot handles the CTA's tiles of sequence number n = slot, slot + 2, ...
+            uint32_t tile = MLP_NO_TILE;
+            uint64_t my_row = 0;
+            const float *bias4 = nullptr;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (l < (uint32_t)(L - 1)) {
-                layer_epilogue<0>(d_t, ahi, alo, cq, bl, bpre, FINE && l == 2u, wd, wc, acc, &a_ready[slot], &bars[MLP_BAR_A_READY2 + slot], lane);
-                if (FINE && l == 2u) dens = acc.x;
-            } else if (FINE) {
-                layer_epilogue<3>(d_t, ahi, alo, cq, bl, bpre, false, wd, wc, acc, &a_ready[slot], &bars[MLP_BAR_A_READY2 + slot], lane);
-                acc.x = dens;
-            } else {
-                layer_epilogue<2>(d_t, ahi, alo, cq, bl, bpre, false, wd, wc, acc, &a_ready[slot], &bars[MLP_BAR_A_READY2 + slot], lane);
-            }
-            // (both arrivals of this layer have been made inside: the slot is back with the issuer)
-            if (l == (uint32_t)(L - 1)) {
-                // ---- heads: combine the four column quarters, activation, store ----
-                // The partial sums of quarters 1..3 travel through TMEM: the first twelve columns of the slot's A region (dead once the
-                // last layer's MMAs are done; next written by the tile's first epilogue, which comes later in every worker's sequence).
-                if (cq != 0u) {
-                    tmem_st4(ahi + 4u * (cq - 1u), reinterpret_cast<const uint32_t *>(&acc));
-                    tmem_st_wait();
-                    fence_before_sync();
+            float2 bpre[8];
+            bias_prefetch(p.bias, h, bpre);  // layer 0: known before the tile is
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
+                tl_mark(p.timeline, lane, warp, 7, n, l);  // ev 7: start waiting for D
+                mbar_wait_backoff(&d_ready[slot], dpar, 32);
+                dpar ^= 1u;
+                fence_after_sync();
+                tl_mark(p.timeline, lane, warp, 8, n, l);  // ev 8: D ready seen
+                if (l == 0) {
+                    tile = tile_ids[n & 7u];
+                    if (tile == MLP_NO_TILE) break;  // retired by the issuer
+                    ++ntl;
+                    my_row = (uint64_t)tile * 128u + q * 32u + (uint32_t)lane;
+                    if (FINE) bias4 = p.dirbias + (size_t)(min(my_row, total_rows - 1) / p.S) * 128;  // per-ray direction bias of this thread's row
                 }
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                if (cq == 0u) {
-                    fence_after_sync();
-                    float4 o1, o2, o3;
-                    tmem_ld4(ahi, reinterpret_cast<uint32_t *>(&o1));
-                    tmem_ld4(ahi + 4u, reinterpret_cast<uint32_t *>(&o2));
-                    tmem_ld4(ahi + 8u, reinterpret_cast<uint32_t *>(&o3));
-                    tmem_ld_wait();
-                    if ((uint64_t)row < total_rows) {
-                        const float sigma = softplus_f(((acc.x + o1.x) + (o2.x + o3.x)) + head_s[512]);
-                        if (FINE) {
-                            reinterpret_cast<float4 *>(p.out)[row] = make_float4(sigma, sigmoid_f(((acc.y + o1.y) + (o2.y + o3.y)) + head_s[513]),
-                                                                                sigmoid_f(((acc.z + o1.z) + (o2.z + o3.z)) + head_s[514]),
-                                                                                sigmoid_f(((acc.w + o1.w) + (o2.w + o3.w)) + head_s[515]));
-                        } else {
-                            p.out[row] = sigma;
-                        }
+                if (l < L - 1) {
+                    layer_epilogue<0>(d_t, ahi, alo, h, p.bias + l * 128, bpre, FINE && l == 2, wd, wc, acc);
+                    // the next layer's first bias chunk: in flight while the next GEMM runs
+                    if (FINE && l == 2) bias_prefetch(bias4, h, bpre); else bias_prefetch(p.bias + (l + 1) * 128, h, bpre);
+                } else if (FINE) {
+                    layer_epilogue<3>(d_t, ahi, alo, h, bias4, bpre, false, wd, wc, acc);
+                } else {
+                    layer_epilogue<2>(d_t, ahi, alo, h, p.bias + 256, bpre, false, wd, wc, acc);
+                }
+                // next A operand written (l < L-1) / accumulator read out and free for the next tile (l == L-1)
+                if (l < L - 1) tmem_st_wait();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[slot]);
+                tl_mark(p.timeline, lane, warp, 9, n, l);  // ev 9: epilogue of layer l done (+arrive)
+            }
+            if (tile == MLP_NO_TILE) break;
+            // ---- heads: combine the two column halves, activation, store ----
+            // The partial sums of the upper column half travel through TMEM: the first four columns of the slot's A region
+            // (dead once the last layer's MMAs are done; next written by this lane quarter's h == 0 warp itself, in the
+            // next tile's first epilogue).
+            if (h == 1) {
+                tmem_st4(ahi, reinterpret_cast<const uint32_t *>(&acc));
+                tmem_st_wait();
+                fence_before_sync();
+            }
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
+            if (h == 0) {
+                fence_after_sync();
+                float4 o;
+                tmem_ld4(ahi, reinterpret_cast<uint32_t *>(&o));
+                tmem_ld_wait();
+                if (my_row < total_rows) {
+                    const float sigma = softplus_f(acc.x + o.x + head_s[512]);
+                    if (FINE) {
+                        reinterpret_cast<float4 *>(p.out)[my_row] = make_float4(sigma, sigmoid_f(acc.y + o.y + head_s[513]),
+                                                                               sigmoid_f(acc.z + o.z + head_s[514]), sigmoid_f(acc.w + o.w + head_s[515]));
+                    } else {
+                        p.out[my_row] = sigma;
                     }
                 }
             }
-            tl_mark(p.timeline, lane, warp, 9, n, l);  // ev 9: epilogue of layer l done
-            const uint32_t nl = l + 1u == (uint32_t)L ? 0u : l + 1u, nn = nl == 0u ? n + 2u : n;
-            pk = nl | ((par ^ 1u) << 3) | (nn << 4);
-            if (slot) { pk1 = pk; row1 = row; dens1 = dens; } else { pk0 = pk; row0 = row; dens0 = dens; }
-            return true;
-        };
-        if (has_work) {
-            if (lane == 0) {  // both accumulators are free for the first tiles
-                mbar_arrive(&a_ready[0]); mbar_arrive(&a_ready[1]);
-                mbar_arrive(&bars[MLP_BAR_A_READY2]); mbar_arrive(&bars[MLP_BAR_A_READY2 + 1]);
-            }
-            // the issuer's order: slot 0 once, then strictly alternating, each slot until it is retired
-            bool alive0 = step(0u), alive1 = true;
-            while (alive0 | alive1) {
-                if (alive0) alive0 = step(0u);
-                if (alive1) alive1 = step(1u);
-            }
+        }
         }
         if (p.timeline != nullptr && threadIdx.x == 0) p.timeline[1000 + 8 * blockIdx.x + 3] = ntl;
     }
