@@ -140,14 +140,17 @@ int tn_render_set_profiling(tn_tracer *h, int enable);
 int tn_render_get_timings(tn_tracer *h, float *ms6);
 /* the same for the last tn_render_train_backward: ms3 = composite_bwd, mlp_bwd, finalize */
 int tn_render_get_backward_timings(tn_tracer *h, float *ms3);
-/* trace_rays picks between bit-identical implementations by batch size (measured crossovers, profiles/r1_trace_sweep.json):
- * >= walk_min_rays (default 10240): adjacency walk, 32 rays per warp (throughput);
- * [lo, hi] below that (default 6144 .. ): adjacency walk, one ray per warp with cooperating lanes;
+/* trace_rays picks between bit-identical implementations by batch size (measured crossovers, profiles/r2_trace_sweep.json):
+ * >= walk_min_rays (default 2^20): adjacency walk, 32 rays per warp (throughput);
+ * solo range [lo, hi] below that (default empty): adjacency walk, one ray per warp with cooperating lanes;
  * otherwise, for meshes that cannot be walked, and as the exact stage the walks fall back to: warp-per-ray all-hits BVH gather. */
 int tn_set_walk_min_rays(tn_tracer *h, uint32_t n);
 int tn_set_walk_solo_range(tn_tracer *h, uint32_t lo, uint32_t hi);
 /* [lo, hi] below walk_min_rays (checked before the solo range): adjacency walk with 8 rays per warp, 4 cooperating lanes per ray */
 int tn_set_walk_quad_range(tn_tracer *h, uint32_t lo, uint32_t hi);
+/* the quad walk of batches of up to n rays (default 10240) loads the records of all candidate next tetrahedra while the current one
+ * is intersected instead of prefetching them (latency-bound regime); 0 = never.  Results are identical. */
+int tn_set_walk_quad_spec_max_rays(tn_tracer *h, uint32_t n);
 /* out2[0] = 1 if the loaded mesh takes the adjacency-walk fast path (conforming, convex hull); out2[1] = rays of the last
  * trace_rays call that needed the exact sort/pairing or all-hits stage.  Synchronises. */
 int tn_debug_trace_stats(tn_tracer *h, uint32_t *out2);

@@ -38,7 +38,8 @@ def medium_mesh():
 TRACE_IMPLS = {
     "walk": (0, (1, 0), (1, 0)),                                  # adjacency walk, 32 rays per warp
     "walk_solo": (2**32 - 1, (0, 2**32 - 1), (1, 0)),             # adjacency walk, one ray per warp
-    "walk_quad": (2**32 - 1, (1, 0), (0, 2**32 - 1)),             # adjacency walk, 8 rays per warp (4 lanes per ray)
+    "walk_quad": (2**32 - 1, (1, 0), (0, 2**32 - 1)),             # adjacency walk, 8 rays per warp (4 lanes per ray), speculative record loads
+    "walk_quad_pf": (2**32 - 1, (1, 0), (0, 2**32 - 1), 0),       # the same with prefetches instead (the form large batches take)
     "bvh": (2**32 - 1, (1, 0), (1, 0)),                           # warp-per-ray all-hits BVH gather
 }
 
@@ -48,3 +49,4 @@ def force_trace_impl(tracer, name):
     tracer.set_walk_min_rays(w[0])
     tracer.set_walk_solo_range(*w[1])
     tracer.set_walk_quad_range(*w[2])
+    tracer.set_walk_quad_spec_max_rays(w[3] if len(w) > 3 else 2**32 - 1)

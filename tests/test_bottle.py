@@ -98,7 +98,7 @@ def test_bottle_reference_invariant(bottle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("impl", ["walk", "walk_solo", "walk_quad", "bvh"])
+@pytest.mark.parametrize("impl", ["walk", "walk_solo", "walk_quad", "walk_quad_pf", "bvh"])
 def test_bottle_gpu_equals_oracle(bottle, impl):
     from tetranerf import cpp
 

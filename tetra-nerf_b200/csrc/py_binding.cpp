@@ -192,6 +192,7 @@ class PyTetrahedraTracer {  // py_binding.cpp:28-227
     void set_walk_min_rays(uint64_t n) { check(tn_set_walk_min_rays(h_, (uint32_t)n)); }
     void set_walk_solo_range(uint64_t lo, uint64_t hi) { check(tn_set_walk_solo_range(h_, (uint32_t)lo, (uint32_t)hi)); }
     void set_walk_quad_range(uint64_t lo, uint64_t hi) { check(tn_set_walk_quad_range(h_, (uint32_t)lo, (uint32_t)hi)); }
+    void set_walk_quad_spec_max_rays(uint64_t n) { check(tn_set_walk_quad_spec_max_rays(h_, (uint32_t)n)); }
     py::tuple trace_stats() {
         uint32_t o2[2] = {0, 0};
         check(tn_debug_trace_stats(h_, o2));
@@ -285,6 +286,7 @@ PYBIND11_MODULE(tetranerf_cpp_extension, m) {  // py_binding.cpp:433-449
         .def("set_walk_min_rays", &PyTetrahedraTracer::set_walk_min_rays)
         .def("set_walk_solo_range", &PyTetrahedraTracer::set_walk_solo_range)
         .def("set_walk_quad_range", &PyTetrahedraTracer::set_walk_quad_range)
+        .def("set_walk_quad_spec_max_rays", &PyTetrahedraTracer::set_walk_quad_spec_max_rays)
         .def("trace_stats", &PyTetrahedraTracer::trace_stats)
         .def("launch_count", &PyTetrahedraTracer::launch_count)
         .def("_check_float_dim3", &PyTetrahedraTracer::check_float_dim3);

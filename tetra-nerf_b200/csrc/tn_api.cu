@@ -158,6 +158,12 @@ extern "C" int tn_set_walk_quad_range(tn_tracer *h, uint32_t lo, uint32_t hi) {
     h->walk_quad_max_rays = hi;
     return TN_OK;
 }
+// quad walk: batches of up to n rays load the records of all candidate next tetrahedra while the current one is intersected (0 = never)
+extern "C" int tn_set_walk_quad_spec_max_rays(tn_tracer *h, uint32_t n) {
+    if (!h) return tn::fail(TN_ERR_ARG, "null tracer");
+    h->walk_quad_spec_max_rays = n;
+    return TN_OK;
+}
 static uint32_t g_last_exact = 0;
 extern "C" uint32_t tn_debug_last_exact_count(void) { return g_last_exact; }
 // test hook: (walkable mesh?, number of rays the last trace_rays call handed to the exact stage); synchronises the device

@@ -106,13 +106,15 @@ struct tn_tracer {
     // trace_rays picks between bit-identical implementations by batch size (measured on B200, 302k tetrahedra, profiles/r2_trace_sweep.json;
     // trace time incl. L2 warm-up, ms at 1024 / 4096 / 8192 / 16384 / 65536 rays):
     //   warp-per-ray all-hits BVH gather   0.19 / 0.31 / 0.57 / 1.02 / 3.51     <- below walk_quad_min_rays
-    //   walk, 8 rays per warp ("quad")     0.30 / 0.31 / 0.32 / 0.45 / 1.56     <- [walk_quad_min_rays, walk_min_rays)
+    //   walk, 8 rays per warp ("quad")     0.27 / 0.27 / 0.30 / 0.45 / 1.56     <- [walk_quad_min_rays, walk_min_rays)  (speculative record
+    //                                                                              loads up to walk_quad_spec_max_rays, prefetches above)
     //   walk, 1 ray per warp ("solo")      0.26 / 0.35 / 0.55 / 1.00 / 3.57     (kept for tests / experiments: range empty by default)
     //   walk, 32 rays per warp             0.66 / 0.67 / 0.68 / 0.81 / 1.95     <- >= walk_min_rays (fewest instructions per ray: only pays off
     //                                                                              once the machine is full several times over)
     uint32_t walk_min_rays = 1u << 20;
     uint32_t walk_solo_min_rays = 1, walk_solo_max_rays = 0;
-    uint32_t walk_quad_min_rays = 4608, walk_quad_max_rays = 0xFFFFFFFFu;
+    uint32_t walk_quad_min_rays = 3584, walk_quad_max_rays = 0xFFFFFFFFu;
+    uint32_t walk_quad_spec_max_rays = 10240;  // quad walk: batches up to this size load the candidate next records speculatively (tn_walk.cu)
     uint64_t launches = 0;
     tn::RenderState *render = nullptr;
 };
@@ -213,6 +215,28 @@ __device__ __forceinline__ bool tri_test(const Sheared &A, const Sheared &B, con
     u = __fmul_rn(V, rcp);
     v = __fmul_rn(W, rcp);
     return (t > 0.0f && t < 1e16f);
+}
+
+// The same test without early exits (identical operation sequence for every value that is returned when the result is `true`):
+// eight rays share a warp in the quad walk, where every data-dependent branch costs a divergence / reconvergence pair per step.
+// The double-precision recomputation of zero edge functions stays a (rare) branch.
+__device__ __forceinline__ bool tri_test_nobranch(const Sheared &A, const Sheared &B, const Sheared &C, float &t, float &u, float &v) {
+    float U = __fsub_rn(__fmul_rn(C.x, B.y), __fmul_rn(C.y, B.x));
+    float V = __fsub_rn(__fmul_rn(A.x, C.y), __fmul_rn(A.y, C.x));
+    float W = __fsub_rn(__fmul_rn(B.x, A.y), __fmul_rn(B.y, A.x));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = __double2float_rn(__dsub_rn(__dmul_rn((double)C.x, (double)B.y), __dmul_rn((double)C.y, (double)B.x)));
+        V = __double2float_rn(__dsub_rn(__dmul_rn((double)A.x, (double)C.y), __dmul_rn((double)A.y, (double)C.x)));
+        W = __double2float_rn(__dsub_rn(__dmul_rn((double)B.x, (double)A.y), __dmul_rn((double)B.y, (double)A.x)));
+    }
+    const bool mixed = (U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f);
+    const float det = __fadd_rn(__fadd_rn(U, V), W);
+    const float Tn = __fadd_rn(__fadd_rn(__fmul_rn(U, A.z), __fmul_rn(V, B.z)), __fmul_rn(W, C.z));
+    const float rcp = __fdiv_rn(1.0f, det);
+    t = __fmul_rn(Tn, rcp);
+    u = __fmul_rn(V, rcp);
+    v = __fmul_rn(W, rcp);
+    return !mixed && det != 0.0f && t > 0.0f && t < 1e16f;
 }
 
 // conservative ray/AABB slab test on a 32-byte BVH node (a = lo.xyz hi.x, b = hi.yz); NaN-safe via fminf/fmaxf

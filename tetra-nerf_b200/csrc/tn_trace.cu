@@ -53,6 +53,7 @@ struct TraceParams {
     // list entries with bit 31 set carry their face hits already (written by the adjacency walk, tn_walk.cu):
     // num[ray] keys at keys_in[ray*M ..]; the gather is skipped and only sort + pairing + emit run
     const u64 *keys_in;
+    int windowed;  // literal pairing restricted to the windows around eps-ties (post_process_windows); 0 = over the whole array (A/B)
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -123,51 +124,164 @@ __device__ void bitonic_sort_keys(u64 *hits, uint32_t nh, int lane) {
     }
 }
 
-// literal post_process_tetrahedra (optix_trace_rays.cu:110-266) on the sorted keys; single lane.
+// literal post_process_tetrahedra (optix_trace_rays.cu:110-266) on the sorted keys.
 // key bit 63 plays hit_distances[].y (the "marked once" flag); face == TN_EMPTY plays t[j] == empty.
 // Every emitted record pairs position j with position j+1 of the array AFTER the swap of :229-235,
 // so only the list of j's is produced; the caller emits (hits[j], hits[j+1]).
-__device__ uint32_t post_process_serial(u64 *key, uint2 *tts, uint32_t n, uint16_t *emit) {
-    const u64 MARK = 1ull << 63;
-    for (uint32_t j = 0; j + 1 < n; ++j) {
-        if (key_face(key[j]) == TN_EMPTY) continue;
-        const float dn = key_t(key[j]);
-        bool clear_self = false;
-        for (uint32_t off = 1; j + off < n && (key_face(key[j + off]) == TN_EMPTY || fabsf(__fsub_rn(key_t(key[j + off]), dn)) < TN_EPS); ++off) {
-            uint32_t cell;
-            if (key_face(key[j + off]) != TN_EMPTY && common_tet(tts[j], tts[j + off], cell)) {
-                if (key_face(key[j]) != key_face(key[j + off])) clear_self = true;
-                if (key[j + off] & MARK) key[j + off] |= 0xFFFFFFFFull;  // already marked once -> delete
-                else key[j + off] |= MARK;
-            }
+// The two loop bodies are functions of j so that the whole-array form (post_process_serial, one lane) and the windowed form
+// (post_process_windows, one lane per window) execute the same statements.
+constexpr u64 KEY_MARK = 1ull << 63;
+// dedupe phase, body of the loop over j (optix_trace_rays.cu:124-159); key[j] is not empty, j + 1 < n
+__device__ __forceinline__ void dedupe_one(u64 *key, const uint2 *tts, uint32_t n, uint32_t j) {
+    const float dn = key_t(key[j]);
+    bool clear_self = false;
+    for (uint32_t off = 1; j + off < n && (key_face(key[j + off]) == TN_EMPTY || fabsf(__fsub_rn(key_t(key[j + off]), dn)) < TN_EPS); ++off) {
+        uint32_t cell;
+        if (key_face(key[j + off]) != TN_EMPTY && common_tet(tts[j], tts[j + off], cell)) {
+            if (key_face(key[j]) != key_face(key[j + off])) clear_self = true;
+            if (key[j + off] & KEY_MARK) key[j + off] |= 0xFFFFFFFFull;  // already marked once -> delete
+            else key[j + off] |= KEY_MARK;
         }
-        if (clear_self && (key[j] & MARK)) key[j] |= 0xFFFFFFFFull;
-        key[j] &= ~MARK;
     }
-    uint32_t jc = 0;
-    for (uint32_t j = 0; j < n; ++j) {
-        if (key_face(key[j]) == TN_EMPTY) continue;
-        const uint2 orig = tts[j];
-        float dn = key_t(key[j]);
-        uint32_t real_offset = 1;
-        for (uint32_t off = 1; j + off < n && (real_offset < 3 || key_face(key[j + off]) == TN_EMPTY ||
-                                               fabsf(__fsub_rn(key_t(key[j + off]), dn)) < TN_EPS); ++off) {
-            if (key_face(key[j + off]) == TN_EMPTY) continue;
-            uint32_t cell;
-            if (common_tet(orig, tts[j + off], cell)) {
-                const bool out = fabsf(__fsub_rn(key_t(key[j]), key_t(key[j + off]))) >= TN_EPS;
-                if (off > 1) {
-                    const u64 tk = key[j + off]; key[j + off] = key[j + 1]; key[j + 1] = tk;
-                    const uint2 tc = tts[j + off]; tts[j + off] = tts[j + 1]; tts[j + 1] = tc;
-                }
-                if (out) emit[jc++] = (uint16_t)j;
-                break;
+    if (clear_self && (key[j] & KEY_MARK)) key[j] |= 0xFFFFFFFFull;
+    key[j] &= ~KEY_MARK;
+}
+// pairing phase, body of the loop over j (optix_trace_rays.cu:161-258); key[j] is not empty.  Returns whether record (j, j+1) is
+// emitted; rd / wr are raised to the largest index the body read / wrote (the swap).
+__device__ __forceinline__ bool pair_one(u64 *key, uint2 *tts, uint32_t n, uint32_t j, uint32_t &rd, uint32_t &wr) {
+    const uint2 orig = tts[j];
+    float dn = key_t(key[j]);
+    uint32_t real_offset = 1, off = 1;
+    bool emitted = false;
+    for (; j + off < n && (real_offset < 3 || key_face(key[j + off]) == TN_EMPTY || fabsf(__fsub_rn(key_t(key[j + off]), dn)) < TN_EPS); ++off) {
+        if (key_face(key[j + off]) == TN_EMPTY) continue;
+        uint32_t cell;
+        if (common_tet(orig, tts[j + off], cell)) {
+            const bool out = fabsf(__fsub_rn(key_t(key[j]), key_t(key[j + off]))) >= TN_EPS;
+            if (off > 1) {
+                const u64 tk = key[j + off]; key[j + off] = key[j + 1]; key[j + 1] = tk;
+                const uint2 tc = tts[j + off]; tts[j + off] = tts[j + 1]; tts[j + 1] = tc;
+                wr = max(wr, j + off);
             }
-            dn = key_t(key[j + off]);
-            real_offset++;
+            emitted = out;
+            break;
         }
+        dn = key_t(key[j + off]);
+        real_offset++;
+    }
+    rd = max(rd, min(j + off, n - 1));
+    return emitted;
+}
+// the whole array on one lane
+__device__ uint32_t post_process_serial(u64 *key, uint2 *tts, uint32_t n, uint16_t *emit) {
+    for (uint32_t j = 0; j + 1 < n; ++j)
+        if (key_face(key[j]) != TN_EMPTY) dedupe_one(key, tts, n, j);
+    uint32_t jc = 0, rd = 0, wr = 0;
+    for (uint32_t j = 0; j < n; ++j)
+        if (key_face(key[j]) != TN_EMPTY && pair_one(key, tts, n, j, rd, wr)) emit[jc++] = (uint16_t)j;
+    return jc;
+}
+
+// Windowed form: the same statements, executed only where they can do something.  Call position j "linked" to j+1 when the two hits
+// are closer than eps or share no tetrahedron.  Away from the runs of links the literal algorithm is the identity pairing: the dedupe
+// body touches nothing (its scan stops at the first hit >= eps away), the pairing body finds its partner at offset 1, emits, swaps
+// nothing.  Around a run of links s..e the dedupe phase marks / deletes only hits within eps of one another (inside the run) and the
+// pairing body of j in [s-1, e] reads at most up to e+2 (real_offset < 3) and swaps inside that range -- so the bodies are run for the
+// windows [s-1, e+2] only, IN ORDER and on ONE lane like the literal loops, and the pairing loop keeps going past a window for as long
+// as its swaps reached (a swapped position is no longer "clean"; such cascades can run to the end of the ray).  The links, the
+// windows, the default decisions and the compaction of the emitted j's are computed by the whole warp.  A typical ray of the walk's
+// exact list has 1-2 windows of ~5 positions among ~170 hits.  mask = 3 * ceil(n / 32) words of shared memory; returns the number
+// of records, their j's in emit[].
+__device__ __forceinline__ uint32_t next_set_bit(const uint32_t *W, uint32_t nw, uint32_t from, uint32_t none) {
+    for (uint32_t c = from >> 5; c < nw; ++c) {
+        uint32_t o = W[c];
+        if (c == (from >> 5)) o &= ~0u << (from & 31u);
+        if (o) return (c << 5) + (uint32_t)__ffs(o) - 1u;
+    }
+    return none;
+}
+__device__ __forceinline__ uint32_t next_clear_bit(const uint32_t *W, uint32_t nw, uint32_t from, uint32_t none) {
+    for (uint32_t c = from >> 5; c < nw; ++c) {
+        uint32_t z = ~W[c];
+        if (c == (from >> 5)) z &= ~0u << (from & 31u);
+        if (z) return (c << 5) + (uint32_t)__ffs(z) - 1u;
+    }
+    return none;
+}
+__device__ __noinline__ uint32_t post_process_windows(u64 *key, uint2 *tts, uint32_t n, uint16_t *emit, uint32_t *mask, int lane) {
+    const uint32_t nw = (n + 31) >> 5;
+    uint32_t *L = mask, *W = mask + nw, *E = mask + 2 * nw;  // links; window / processed positions; emitted positions
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t j = base + lane;
+        bool link = false;
+        if (j + 1 < n) {
+            uint32_t cell;
+            link = fabsf(__fsub_rn(key_t(key[j + 1]), key_t(key[j]))) < TN_EPS || !common_tet(tts[j], tts[j + 1], cell);
+        }
+        const uint32_t w = __ballot_sync(FULL, link);
+        if (lane == 0) { L[base >> 5] = w; E[base >> 5] = 0u; }
+    }
+    __syncwarp();
+    for (uint32_t c = lane; c < nw; c += 32) {  // W[j] = OR of link[j-3 .. j+1]
+        const uint32_t l = L[c], lp = c ? L[c - 1] : 0u, ln = c + 1 < nw ? L[c + 1] : 0u;
+        uint32_t w = l | (l >> 1) | (ln << 31) | (l << 1) | (lp >> 31) | (l << 2) | (lp >> 30) | (l << 3) | (lp >> 29);
+        if (c == nw - 1 && (n & 31u)) w &= (1u << (n & 31u)) - 1u;  // positions >= n: clear (so that every run ends inside the array)
+        W[c] = w;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        // dedupe phase (the loop of :124-159) over the windows
+        for (uint32_t ws = next_set_bit(W, nw, 0, n); ws < n;) {
+            const uint32_t we = min(next_clear_bit(W, nw, ws, n), n) - 1u;  // last position of the run
+            for (uint32_t j = ws; j <= we && j + 1 < n; ++j)
+                if (key_face(key[j]) != TN_EMPTY) dedupe_one(key, tts, n, j);
+            ws = next_set_bit(W, nw, we + 1, n);
+        }
+        // pairing phase (the loop of :161-258) over the windows and whatever their swaps reach
+        for (uint32_t ws = next_set_bit(W, nw, 0, n); ws < n;) {
+            const uint32_t we = min(next_clear_bit(W, nw, ws, n), n) - 1u;
+            uint32_t lim = we, rd = 0, wr = 0;
+            for (uint32_t j = ws; j <= lim && j < n; ++j) {
+                const bool em = key_face(key[j]) != TN_EMPTY && pair_one(key, tts, n, j, rd, wr);
+                lim = max(lim, wr);
+                if (j > we) W[j >> 5] |= 1u << (j & 31u);  // processed here although outside the window
+                if (em) E[j >> 5] |= 1u << (j & 31u);
+            }
+            ws = next_set_bit(W, nw, lim + 1, n);
+        }
+    }
+    __syncwarp();
+    uint32_t jc = 0;
+    for (uint32_t base = 0; base < n; base += 32) {  // compact: processed positions as decided above, the others pair with their successor
+        const uint32_t j = base + lane;
+        const uint32_t w = W[base >> 5], e = E[base >> 5];
+        const bool em = ((w >> lane) & 1u) ? ((e >> lane) & 1u) != 0u : (j + 1 < n);
+        const uint32_t m = __ballot_sync(FULL, em);
+        if (em) emit[jc + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+        jc += __popc(m);
     }
     return jc;
+}
+
+// keys that are sorted up to a few local inversions (the walk's keys: ties only): odd-even transposition passes, bitonic if they do
+// not suffice.  Keys are distinct, so every correct sort gives the same array.
+__device__ void bitonic_sort_keys(u64 *hits, uint32_t nh, int lane);
+__device__ __noinline__ void sort_nearly_sorted(u64 *hits, uint32_t nh, int lane) {
+    for (int pass = 0; pass < 5; ++pass) {
+        bool inv = false;
+        for (uint32_t j = lane; j + 1 < nh; j += 32) inv |= hits[j] > hits[j + 1];
+        if (!__any_sync(FULL, inv)) return;
+        if (pass == 4) break;
+        for (uint32_t par = 0; par < 2; ++par) {
+            __syncwarp();
+            for (uint32_t i = 2 * lane + par; i + 1 < nh; i += 64) {
+                const u64 a = hits[i], b = hits[i + 1];
+                if (a > b) { hits[i] = b; hits[i + 1] = a; }
+            }
+        }
+        __syncwarp();
+    }
+    bitonic_sort_keys(hits, nh, lane);
 }
 
 template <int MODE>  // 0: trace_rays (tetrahedra), 1: trace_rays_triangles (sorted raw face hits)
@@ -296,7 +410,10 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 7) k_trace(const TraceParams
         if (nh > M - 1) rank_select(hits, nh, M - 1, lane);  // (phase 1 never gets here with nh > hcap - 4 >= ... it defers first)
 
         // ---------------- 2. sort by (t, face id) ----------------
-        if (nh > 1) bitonic_sort_keys(hits, nh, lane);
+        if (nh > 1) {
+            if (provided) sort_nearly_sorted(hits, nh, lane);
+            else bitonic_sort_keys(hits, nh, lane);
+        }
         __syncwarp();
 
         const size_t row = (size_t)ray * M;
@@ -352,8 +469,18 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 7) k_trace(const TraceParams
                         jc += __popc(mask);
                     }
                 } else {
-                    if (lane == 0) jc = post_process_serial(hits, tts, nh, emit);
-                    jc = __shfl_sync(FULL, jc, 0);
+                    // rays with eps-ties that are not isolated (5-6 % of a batch): the literal algorithm restricted to the windows around
+                    // the ties; the mask words live behind tts[] in the work-list region when it has room
+                    bool windowed = false;
+                    const uint32_t nw = (nh + 31u) >> 5;
+                    if (p.windowed && (size_t)nh * 8 + (size_t)nw * 12 <= (size_t)p.scap * 4) {
+                        jc = post_process_windows(hits, tts, nh, emit, reinterpret_cast<uint32_t *>(tts + nh), lane);
+                        windowed = true;
+                    }
+                    if (!windowed) {
+                        if (lane == 0) jc = post_process_serial(hits, tts, nh, emit);
+                        jc = __shfl_sync(FULL, jc, 0);
+                    }
                 }
                 __syncwarp();
             }
@@ -466,6 +593,8 @@ static int launch_trace(tn_tracer *h, int mode, const float *o, const float *d, 
     p.o = o; p.d = d; p.R = R; p.M = M; p.num = num; p.cells = cells; p.bary = bary; p.dist = dist; p.verts = verts;
     p.nodes = h->mesh.nodes; p.leaves = h->mesh.leaves; p.tri = (const uint4 *)h->mesh.tri; p.tt = (const uint2 *)h->mesh.tt;
     p.xyz = h->mesh.xyz; p.lv = h->mesh.lv; p.absmax = h->mesh.absmax; p.dense = dense; p.flags = h->d_flags;
+    static const int windowed_env = [] { const char *e = getenv("TETRANERF_B200_WINDOWED_PAIRING"); return e ? atoi(e) : 1; }();  // A/B switch
+    p.windowed = windowed_env;
     auto kern = mode == 0 ? k_trace<0> : k_trace<1>;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);

@@ -368,7 +368,13 @@ __global__ void __launch_bounds__(32) k_walk_coop(const WalkParams p) {
 // step and how many chains are in flight per scheduler.  One ray per warp (k_walk_coop) issues a full warp instruction stream per
 // ray (28 warps per SM fight for issue slots); 32 rays per warp (k_walk) leaves 128 warps for 148 SMs.  Here a warp instruction
 // stream serves 8 rays: lane j of a quad owns vertex j and the face opposite to it, exactly as in k_walk_coop.
+// SPEC: the records of all candidate next tetrahedra (the neighbours across the three faces the ray did not enter through) are LOADED
+// while the current one is intersected and the right one is selected afterwards, instead of prefetched into L1: ncu (round 2) put 25 %
+// of the walk's stall samples on the first use of the next record although it had been prefetched a step earlier.  Three times the L2
+// traffic of the walk, which is irrelevant while the walk is latency-bound (batches that do not fill the machine); large batches keep
+// the prefetch.
 constexpr int QUAD_WARPS = 2;  // 64 threads = 16 rays per block: 256 blocks for 4096 rays, spread over all SMs
+template <bool SPEC>
 __global__ void __launch_bounds__(QUAD_WARPS * 32) k_walk_quad(const WalkParams p) {
     __shared__ uint32_t s_stack[QUAD_WARPS * 8][8 * TN_MAX_LEVELS + 8];
     constexpr unsigned FULLM = 0xffffffffu;
@@ -468,22 +474,44 @@ __global__ void __launch_bounds__(QUAD_WARPS * 32) k_walk_quad(const WalkParams 
     float t_in = __uint_as_float((uint32_t)(best >> 32)), u_in = bu, v_in = bv;
     bool generic = true, exact = false, prev_small = false, walking = live;
     if (live && lq == 0) p.keys[row] = best;
-    while (__any_sync(FULLM, walking)) {
-        const float4 *wp = reinterpret_cast<const float4 *>(p.walk + c);
+    // this lane's part of the current tetrahedron's record (SPEC: carried from the previous step's speculative loads)
+    float4 vj = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t nbj = TN_EMPTY, vidj = 0;
+    uint2 wp2 = make_uint2(0u, 0u);
+    auto load_rec = [&](uint32_t tet, float4 &v, uint32_t &nb, uint32_t &vid, uint2 &w2) {
+        const float4 *wp = reinterpret_cast<const float4 *>(p.walk + tet);
         const uint32_t *wq = reinterpret_cast<const uint32_t *>(wp);
-        float4 vj = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t nbj = TN_EMPTY, vidj = 0, wind = 0, perm = 0;
-        if (walking) {
-            vj = __ldg(wp + lq);                  // vertex lq + the face id opposite to it
-            nbj = __ldg(wq + 16 + lq);            // neighbour across my face
-            vidj = __ldg(wq + 20 + lq);           // my vertex id
-            const uint2 wp2 = __ldg(reinterpret_cast<const uint2 *>(wp + 7));
-            wind = wp2.x; perm = wp2.y;
-            if (nbj != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nbj));  // the next record is one of the neighbours
+        v = __ldg(wp + lq);                  // vertex lq + the face id opposite to it
+        nb = __ldg(wq + 16 + lq);            // neighbour across my face
+        vid = __ldg(wq + 20 + lq);           // my vertex id
+        w2 = __ldg(reinterpret_cast<const uint2 *>(wp + 7));
+    };
+    if (SPEC && walking) load_rec(c, vj, nbj, vidj, wp2);
+    while (__any_sync(FULLM, walking)) {
+        const uint32_t *wq = reinterpret_cast<const uint32_t *>(p.walk + c);
+        if (!SPEC) {
+            vj = make_float4(0.f, 0.f, 0.f, 0.f); nbj = TN_EMPTY; vidj = 0; wp2 = make_uint2(0u, 0u);
+            if (walking) {
+                load_rec(c, vj, nbj, vidj, wp2);
+                if (nbj != TN_EMPTY) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.walk + nbj));  // the next record is one of the neighbours
+            }
         }
+        const uint32_t wind = wp2.x, perm = wp2.y;
         const uint32_t fwj = __float_as_uint(vj.w);
         const uint32_t inm = (__ballot_sync(FULLM, walking && (fwj & TN_FACE_MASK) == fin) >> gbase) & 0xFu;  // entry face
         jin = inm ? (uint32_t)__ffs(inm) - 1u : 3u;
+        // SPEC: this lane's part of every candidate next record, in flight while the faces are tested
+        float4 cv[4];
+        uint32_t cnb[4], cvid[4];
+        uint2 cw[4];
+        if (SPEC) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t nk = __shfl_sync(FULLM, nbj, gbase + k);
+                cv[k] = make_float4(0.f, 0.f, 0.f, 0.f); cnb[k] = TN_EMPTY; cvid[k] = 0; cw[k] = make_uint2(0u, 0u);
+                if (walking && (uint32_t)k != jin && nk != TN_EMPTY) load_rec(nk, cv[k], cnb[k], cvid[k], cw[k]);
+            }
+        }
         const Sheared sj = shear(rs, vj.x, vj.y, vj.z);
         const uint32_t w = (wind >> (6 * lq)) & 63u;  // stored winding of my face as local vertex indices
         const uint32_t a = gbase + (w & 3u), b = gbase + ((w >> 2) & 3u), cc = gbase + ((w >> 4) & 3u);
@@ -492,7 +520,8 @@ __global__ void __launch_bounds__(QUAD_WARPS * 32) k_walk_quad(const WalkParams 
         B.x = __shfl_sync(FULLM, sj.x, b); B.y = __shfl_sync(FULLM, sj.y, b); B.z = __shfl_sync(FULLM, sj.z, b);
         Cv.x = __shfl_sync(FULLM, sj.x, cc); Cv.y = __shfl_sync(FULLM, sj.y, cc); Cv.z = __shfl_sync(FULLM, sj.z, cc);
         float t = 0.f, u = 0.f, v = 0.f;
-        const bool hit = walking && lq != jin && tri_test(A, B, Cv, t, u, v);
+        const bool tri = tri_test_nobranch(A, B, Cv, t, u, v);
+        const bool hit = walking && lq != jin && tri;
         const uint32_t hm = (__ballot_sync(FULLM, hit) >> gbase) & 0xFu;
         const bool one = __popc(hm) == 1;
         const uint32_t jout = hm ? (uint32_t)__ffs(hm) - 1u : 0u;
@@ -529,7 +558,15 @@ __global__ void __launch_bounds__(QUAD_WARPS * 32) k_walk_quad(const WalkParams 
                 nfaces++;
                 if (next == TN_EMPTY) walking = false;                              // left the mesh
                 else if (nfaces >= p.M - 1) { exact = true; walking = false; }      // truncated by the hit cap: exact stage (see k_walk)
-                else { c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out; }
+                else {
+                    c = next; fin = fout; t_in = t_out; u_in = u_out; v_in = v_out;
+                    if (SPEC) {  // the record of the tetrahedron behind the exit face has been loaded already
+                        vj = jout == 0u ? cv[0] : (jout == 1u ? cv[1] : (jout == 2u ? cv[2] : cv[3]));
+                        nbj = jout == 0u ? cnb[0] : (jout == 1u ? cnb[1] : (jout == 2u ? cnb[2] : cnb[3]));
+                        vidj = jout == 0u ? cvid[0] : (jout == 1u ? cvid[1] : (jout == 2u ? cvid[2] : cvid[3]));
+                        wp2 = jout == 0u ? cw[0] : (jout == 1u ? cw[1] : (jout == 2u ? cw[2] : cw[3]));
+                    }
+                }
             }
         }
     }
@@ -570,7 +607,8 @@ int launch_walk(tn_tracer *h, const float *o, const float *d, uint32_t R, uint32
     p.walk = h->mesh.walk; p.hull_nodes = h->mesh.hull_nodes; p.hull_leaves = h->mesh.hull_leaves; p.hull_tet = h->mesh.hull_tet;
     p.hlv = h->mesh.hull_lv; p.absmax = h->mesh.absmax; p.keys = keys; p.list = list; p.list_count = list_count;
     if (kind == 1) k_walk_coop<<<R, 32, 0, s>>>(p);                                                           // one ray per warp
-    else if (kind == 2) k_walk_quad<<<(R + QUAD_WARPS * 8 - 1) / (QUAD_WARPS * 8), QUAD_WARPS * 32, 0, s>>>(p);  // 8 rays per warp
+    else if (kind == 2 && R <= h->walk_quad_spec_max_rays) k_walk_quad<true><<<(R + QUAD_WARPS * 8 - 1) / (QUAD_WARPS * 8), QUAD_WARPS * 32, 0, s>>>(p);   // 8 rays per warp, speculative record loads
+    else if (kind == 2) k_walk_quad<false><<<(R + QUAD_WARPS * 8 - 1) / (QUAD_WARPS * 8), QUAD_WARPS * 32, 0, s>>>(p);  // 8 rays per warp
     else k_walk<<<(R + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(p);                             // 32 rays per warp
     h->launches += 1;
     TN_CUDA(cudaGetLastError());

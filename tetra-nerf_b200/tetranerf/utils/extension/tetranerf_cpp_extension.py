@@ -40,6 +40,7 @@ _lib.tn_debug_trace_stats.argtypes = [_vp, C.POINTER(_u32)]
 _lib.tn_set_walk_min_rays.argtypes = [_vp, _u32]
 _lib.tn_set_walk_solo_range.argtypes = [_vp, _u32, _u32]
 _lib.tn_set_walk_quad_range.argtypes = [_vp, _u32, _u32]
+_lib.tn_set_walk_quad_spec_max_rays.argtypes = [_vp, _u32]
 _lib.tn_launch_count.restype = C.c_uint64
 _lib.tn_launch_count.argtypes = [_vp]
 
@@ -151,6 +152,10 @@ class TetrahedraTracer:
     def set_walk_quad_range(self, lo: int, hi: int) -> None:
         """batches below walk_min_rays with lo <= rays <= hi use the 8-rays-per-warp form of the walk (lo > hi = never); checked before the solo range"""
         _check(_lib.tn_set_walk_quad_range(self._h, int(lo), int(hi)))
+
+    def set_walk_quad_spec_max_rays(self, n: int) -> None:
+        """quad walk: batches of up to n rays load all candidate next records speculatively instead of prefetching them (0 = never)"""
+        _check(_lib.tn_set_walk_quad_spec_max_rays(self._h, int(n)))
 
     def trace_stats(self):
         """(walkable mesh?, rays of the last trace_rays that took the exact stage) -- test/diagnostic hook"""

@@ -10,6 +10,7 @@ if len(sys.argv) > 1:
     dev = torch.device("cuda:0")
     V, C, field = bench.make_workload()
     tr = cpp.TetrahedraTracer(dev); dV, dC = torch.from_numpy(V).to(dev), torch.from_numpy(C).to(dev); tr.load_tetrahedra(dV, dC)
+    if "TN_SWEEP_SPEC" in os.environ: tr.set_walk_quad_spec_max_rays(int(os.environ["TN_SWEEP_SPEC"]))
     fr = FusedRenderer(tr); fr.set_field(torch.from_numpy(field).to(dev)); fr.set_weights(bench.mlp_params()); fr.set_profiling(True)
     st = RenderSettings.tetra_nerf()
     res = {}
@@ -22,7 +23,9 @@ if len(sys.argv) > 1:
         res[n] = {k: round(float(np.median([x[k] for x in t])), 4) for k in t[0]}
     print(json.dumps(res))
 else:
-    for mode in ("0", "1", "2", "3"):  # BVH gather, walk 32 rays/warp, walk 1 ray/warp, walk 8 rays/warp
+    # BVH gather, walk 32 rays/warp, walk 1 ray/warp, walk 8 rays/warp (prefetching / speculative record loads)
+    for mode, spec in (("0", None), ("1", None), ("2", None), ("3", "0"), ("3", str(2**32 - 1))):
         env = dict(os.environ, TETRANERF_B200_WALK=mode)
+        if spec is not None: env["TN_SWEEP_SPEC"] = spec
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print("WALK=" + mode, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:])
+        print("WALK=" + mode + ("" if spec is None else "/spec=" + spec), out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:])

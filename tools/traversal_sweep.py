@@ -51,7 +51,7 @@ for gen_name, gen in (("camera", syn.camera_rays), ("sphere", syn.sphere_rays)):
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(ksum, op=dist.ReduceOp.SUM)
         ms, sumK = float(tmax.item()), int(ksum.item())
         B = 28 * R * world + 52 * sumK + world * (12 * len(V) + 16 * len(C) + 20 * F)
-        impl = "bvh gather" if R < 4608 else ("walk, 8 rays/warp" if R < (1 << 20) else "walk, 32 rays/warp")
+        impl = "bvh gather" if R < 3584 else ("walk, 8 rays/warp" if R < (1 << 20) else "walk, 32 rays/warp")
         row = {"rays": gen_name, "R_per_gpu": R, "ms": round(ms, 4), "mean_K": round(sumK / (R * world), 1), "rays_per_s": round(R * world / ms * 1e3),
                "algorithmic_MB": round(B / 1e6, 1), "achieved_GBs": round(B / ms / 1e6, 1), "frac_of_hbm_peak": round(B / ms / 1e6 / (peak * world), 4), "impl": impl}
         if rank == 0:
