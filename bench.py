@@ -55,9 +55,9 @@ def synthetic():
     return mod
 
 
-def workload_config(workload: str, mode: str, rays: int, world: int, tetrahedra: int):
+def workload_config(workload: str, mode: str, rays: int, world: int, tetrahedra: int, points: int = NUM_POINTS):
     """the `config` object: identical for both arms"""
-    return {"workload": f"delaunay45k_302ktet/{rays}rays/{WORKLOADS[workload]['tag']}/{'train-fwd+bwd' if mode == 'train' else 'eval-forward'}",
+    return {"workload": f"delaunay{points // 1000}k_{round(tetrahedra / 1000)}ktet/{rays}rays/{WORKLOADS[workload]['tag']}/{'train-fwd+bwd' if mode == 'train' else 'eval-forward'}",
             "tetrahedra": int(tetrahedra), "rays_per_step_per_gpu": int(rays),
             "parallelism": f"ray-shard x{world} (weak scaling), mesh+weights replicated, NCCL all_gather of pixels"}
 
@@ -550,7 +550,7 @@ def run_train(args, rank, world, dev, V, C, field, params, dist):
             "metric": "rays/sec (train step fwd+bwd+optimizer, 8192-ray batch, ~2M-tet mesh)", "value": total / (ms_total * 1e-3), "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (trace/interp/compositing/optimizer) + bf16x3 tensor-core MLP fwd+bwd with f32 accumulate",
-            "data": "synthetic", "config": workload_config(args.workload, "train", R, world, len(C)) | {"points": int(len(V))},
+            "data": "synthetic", "config": workload_config(args.workload, "train", R, world, len(C), int(len(V))) | {"points": int(len(V))},
             "timing": {"l2": "flushed between timed steps (256 MiB fill); a new ray batch every step", "events": "CUDA events per step on the launch stream, max over ranks",
                        "step": "TetrahedraNerf.forward (training mode) -> MSE loss -> backward -> (N>1: gradient all-reduce) -> RAdam step"},
             "roofline": {"kernel": "whole training step", "bound": "tensor", "unit": "TFLOP/s", "achieved": ach, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],

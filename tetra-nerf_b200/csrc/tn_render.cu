@@ -223,8 +223,9 @@ __device__ __forceinline__ float linspace_f(float start, float end, uint32_t ste
     return i < steps / 2 ? start + step * (float)i : end - step * (float)(steps - i - 1);
 }
 
-// find_visited_cells for one sample distance d against staged segments (t_in, t_out, prefix-max of t_out)
-__device__ __forceinline__ void match_sample(float d, uint32_t n, const float *t_in, const float *t_out, const float *pm, size_t row,
+// find_visited_cells for one sample distance d: binary search over the staged prefix-max of t_out, then the segment's own
+// (t_in, t_out) from the trace output (L1: the warp has just read the row)
+__device__ __forceinline__ void match_sample(float d, uint32_t n, const float2 *__restrict__ dist, const float *pm, size_t row,
                                              const uint4 *__restrict__ verts, const float *__restrict__ bary, uint4 &vi, float &b0,
                                              float &b1, float &b2) {
     vi = make_uint4(TN_EMPTY, TN_EMPTY, TN_EMPTY, TN_EMPTY);
@@ -234,9 +235,11 @@ __device__ __forceinline__ void match_sample(float d, uint32_t n, const float *t
         const uint32_t mid = (lo + hi) >> 1;
         if (pm[mid] < d) lo = mid + 1; else hi = mid;
     }
-    if (lo < n && t_in[lo] <= d) {
+    if (lo >= n) return;
+    const float2 h = __ldg(dist + row + lo);
+    if (h.x <= d) {
         vi = __ldg(verts + row + lo);
-        const float mult = __fdiv_rn(__fsub_rn(d, t_in[lo]), __fsub_rn(t_out[lo], t_in[lo]));
+        const float mult = __fdiv_rn(__fsub_rn(d, h.x), __fsub_rn(h.y, h.x));
         const float omm = __fsub_rn(1.0f, mult);
         const float *c = bary + 6 * (row + lo);
         b0 = __fadd_rn(__fmul_rn(omm, __ldg(c)), __fmul_rn(mult, __ldg(c + 3)));
@@ -245,11 +248,14 @@ __device__ __forceinline__ void match_sample(float d, uint32_t n, const float *t
     }
 }
 
-// shared memory per warp: 3 segment arrays (t_in t_out pm) of M+2 floats and 4 bin/weight arrays (aux e x y) of
-// max(Smax, M when the biased sampler needs cum[M+1]) + 2 floats
+// shared memory per warp.  Only the prefix-max of t_out (binary-searched by every sample) is staged per segment; t_in / t_out are
+// read from the trace output where needed.  Coarse pass: pm[M+2], cum[M+2] (biased sampler only), e[Sc+2] = 4.6 KB at M = 512,
+// Sc = 128; fine pass: pm[M+2] and cdf / e / x / y of Smax+2 = 6.2 KB -- every ray of a 4096-ray batch is resident at once
+// (28 warps per SM; round 1 staged three segment arrays and sized all bin arrays for the worst case: 14.4 / 10.3 KB per warp,
+// 12 / 20 warps per SM, i.e. the coarse pass ran in 2.3 waves).
 __host__ __device__ __forceinline__ size_t seg_arr(uint32_t M) { return (size_t)M + 2; }
-__host__ __device__ __forceinline__ size_t bin_arr(uint32_t M, uint32_t Smax, uint32_t biased) { return (size_t)((biased && M > Smax) ? M : Smax) + 2; }
-__host__ __device__ __forceinline__ size_t sample_floats(uint32_t M, uint32_t Smax, uint32_t biased) { return 3 * seg_arr(M) + 4 * bin_arr(M, Smax, biased); }
+__host__ __device__ __forceinline__ size_t coarse_floats(uint32_t M, uint32_t Sc, uint32_t biased) { return seg_arr(M) * (biased ? 2 : 1) + (size_t)Sc + 2; }
+__host__ __device__ __forceinline__ size_t fine_floats(uint32_t M, uint32_t Smax) { return seg_arr(M) + 4 * ((size_t)Smax + 2); }
 
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const SampleParams p) {
     extern __shared__ float sm[];
@@ -257,9 +263,9 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const Sampl
     const uint32_t ray = blockIdx.x * SAMPLE_WARPS + warp;
     if (ray >= p.R) return;
     const uint32_t M = p.M, S = p.Sc;
-    const size_t A = seg_arr(M), B = bin_arr(M, max(p.Sc, p.S2), 1);
-    float *t_in = sm + (size_t)warp * (3 * A + 4 * B);
-    float *t_out = t_in + A, *pm = t_out + A, *cum = pm + A, *e = cum + B;
+    const size_t A = seg_arr(M);
+    float *pm = sm + (size_t)warp * coarse_floats(M, S, p.biased);
+    float *cum = pm + A, *e = cum + (p.biased ? A : 0);
     const uint32_t n = p.num[ray];
     if (n == 0) {  // model.py:640-650 : background colour, accumulation 0, depth = collider far plane
         store_pixel(p, ray, lane, p.bg0, p.bg1, p.bg2, 0.f, p.far_plane, 0);
@@ -269,14 +275,16 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const Sampl
     if (lane == 0) { slot = atomicAdd(p.n_active, 1u); p.ray_list[slot] = ray; p.mask[ray] = 1; }
     slot = __shfl_sync(0xffffffffu, slot, 0);
     const size_t row = (size_t)ray * M;
-    for (uint32_t k = lane; k < n; k += 32) { const float2 h = p.dist[row + k]; t_in[k] = h.x; t_out[k] = h.y; }
+    const float near = __ldg(&p.dist[row]).x, far = __ldg(&p.dist[row + n - 1]).y;
+    for (uint32_t k = lane; k < n; k += 32) {
+        const float2 h = __ldg(&p.dist[row + k]);
+        pm[k] = h.y;
+        if (p.biased) cum[k + 1] = fmaxf(h.y - h.x, 0.f);  // map_from_real_distances_to_biased_with_bounds, model.py:111-122
+    }
+    if (p.biased && lane == 0) cum[0] = near;
     __syncwarp();
-    const float near = t_in[0], far = t_out[n - 1];
-    smem_scan_max(t_out, pm, n, lane);
-    if (p.biased) {  // map_from_real_distances_to_biased_with_bounds, model.py:111-122
-        if (lane == 0) cum[0] = near;
-        for (uint32_t k = lane; k < n; k += 32) cum[k + 1] = fmaxf(t_out[k] - t_in[k], 0.f);
-        __syncwarp();
+    smem_scan_max(pm, pm, n, lane);  // in place
+    if (p.biased) {
         // cum[k] = start + sum_{i<k} len_i : scan over [start, len_0, len_1, ...]
         smem_scan_add(cum, n + 1, lane);
     }
@@ -296,7 +304,8 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const Sampl
             iv = fmaxf(iv, 0.f);
             rest = rest - iv;
             const uint32_t k = (uint32_t)iv;
-            const float len = fmaxf(t_out[k] - t_in[k], 0.f);
+            const float2 hk = __ldg(&p.dist[row + k]);
+            const float len = fmaxf(hk.y - hk.x, 0.f);
             eu = cum[k] + len * rest;
             sb = (eu - near) / (far - near);  // model.py:182
         }
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_coarse(const Sampl
     for (uint32_t j = lane; j < S; j += 32) {
         const float dmid = (e[j + 1] + e[j]) / 2.f;  // model.py:557
         uint4 vi; float b0, b1, b2;
-        match_sample(dmid, n, t_in, t_out, pm, row, p.verts, p.bary, vi, b0, b1, b2);
+        match_sample(dmid, n, p.dist, pm, row, p.verts, p.bary, vi, b0, b1, b2);
         const size_t g = (size_t)slot * S + j;
         p.vi_c[g] = vi;
         p.bary_c[3 * g] = b0; p.bary_c[3 * g + 1] = b1; p.bary_c[3 * g + 2] = b2;
@@ -368,16 +377,16 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_fine(const SampleP
     const uint32_t slot = blockIdx.x * SAMPLE_WARPS + warp;
     if (slot >= *p.n_active) return;
     const uint32_t M = p.M, S = p.Sc, S2 = p.S2, nb = p.Sf + 1;
-    const size_t A = seg_arr(M), B = bin_arr(M, max(p.Sc, p.S2), 0);
-    float *t_in = sm + (size_t)warp * (3 * A + 4 * B);
-    float *t_out = t_in + A, *pm = t_out + A, *cdf = pm + A, *e = cdf + B, *x = e + B, *y = x + B;
+    const size_t A = seg_arr(M), B = (size_t)max(p.Sc, p.S2) + 2;
+    float *pm = sm + (size_t)warp * fine_floats(M, max(p.Sc, p.S2));
+    float *cdf = pm + A, *e = cdf + B, *x = e + B, *y = x + B;
     const uint32_t ray = p.ray_list[slot];
     const uint32_t n = p.num[ray];
     const size_t row = (size_t)ray * M;
-    for (uint32_t k = lane; k < n; k += 32) { const float2 h = p.dist[row + k]; t_in[k] = h.x; t_out[k] = h.y; }
+    const float near = __ldg(&p.dist[row]).x, far = __ldg(&p.dist[row + n - 1]).y;
+    for (uint32_t k = lane; k < n; k += 32) pm[k] = __ldg(&p.dist[row + k]).y;
     __syncwarp();
-    const float near = t_in[0], far = t_out[n - 1];
-    smem_scan_max(t_out, pm, n, lane);
+    smem_scan_max(pm, pm, n, lane);  // in place
     // ---- coarse weights (model.py:581-582) ----
     const float *eb = p.ebins_c + (size_t)slot * (S + 1);
     const float *sbc = p.sbins_c + (size_t)slot * (S + 1);
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) k_sample_fine(const SampleP
     for (uint32_t j = lane; j < S2; j += 32) {
         const float dmid = (y[j + 1] + y[j]) / 2.f;  // model.py:585
         uint4 vi; float b0, b1, b2;
-        match_sample(dmid, n, t_in, t_out, pm, row, p.verts, p.bary, vi, b0, b1, b2);
+        match_sample(dmid, n, p.dist, pm, row, p.verts, p.bary, vi, b0, b1, b2);
         const size_t g = (size_t)slot * S2 + j;
         p.vi_f[g] = vi;
         p.bary_f[3 * g] = b0; p.bary_f[3 * g + 1] = b1; p.bary_f[3 * g + 2] = b2;
@@ -730,8 +739,8 @@ static int render_impl(tn_tracer *h, const tn_render_config *cfg, const float *d
         p.gather_world = r->gather_world; p.gather_rank = r->gather_rank; p.gather_stride = r->gather_stride;
     }
     const uint32_t Smax = std::max(Sc, S2);
-    const size_t smem_sc = SAMPLE_WARPS * sizeof(float) * sample_floats(M, Smax, 1);  // coarse: cum[] has M+1 entries
-    const size_t smem_sf = SAMPLE_WARPS * sizeof(float) * sample_floats(M, Smax, 0);
+    const size_t smem_sc = SAMPLE_WARPS * sizeof(float) * coarse_floats(M, Sc, p.biased);
+    const size_t smem_sf = SAMPLE_WARPS * sizeof(float) * fine_floats(M, Smax);
     const size_t smem_c = SAMPLE_WARPS * sizeof(float) * 2 * ((size_t)S2 + 2);
     TN_CUDA(cudaFuncSetAttribute(k_sample_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
     TN_CUDA(cudaFuncSetAttribute(k_sample_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sf));
