@@ -173,6 +173,10 @@ int tn_debug_mma_rate(int device, int nrep, int mode, uint32_t boff, long long *
  * zeroed by the caller; [1..n] = (tag << 40 | clock) records of CTA 0, [1000 + 8 b ..] per-CTA start/end/smid/tile counts.
  * NULL switches it off. */
 int tn_debug_set_timeline(void *d_buf);
+/* CTA-pair (cta_group::2) MMA bring-up / rate probe: out[256,128] = P[256,128] Q[128,128]^T with bf16x3 products on a 2-CTA cluster
+ * (M = 256, N = 128 per instruction, each CTA holds half of B); ts != 0 takes the A operand from TMEM; bswap swaps the B halves;
+ * h_cyc = {issue cycles, issue + completion} of nrep x 24 MMAs. */
+int tn_debug_cg2(int device, int nrep, int bswap, int ts, const float *d_P, const float *d_Q, float *d_out, long long *h_cyc);
 /* rays of the last tn_debug_trace_stats call that needed the all-hits gather (subset of out2[1]) */
 uint32_t tn_debug_last_exact_count(void);
 

@@ -246,6 +246,147 @@ __global__ void __launch_bounds__(160, 1) k_debug_gemm2(const float *__restrict_
 }
 }  // namespace tn
 
+// ---- CTA-pair MMA (cta_group::2): bring-up + rate probe ----------------------------------------------------------------------
+// out[256,128] = P[256,128] Q[128,128]^T with bf16x3 products.  Two CTAs of one cluster: CTA r holds A rows 128r..128r+127 and
+// HALF of B (64 of the 128 rows of Q); the leader (rank 0) issues M = 256, N = 128 MMAs, the accumulator rows 128r.. land in CTA
+// r's TMEM, one multicast commit releases the epilogue warps of both CTAs.  ts != 0: the A operand comes from TMEM (each CTA
+// copies its hi / lo A rows into its own TMEM columns 128.. first).  nrep > 1 repeats the 24 MMAs (accumulating) for the rate.
+namespace tn {
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t ncols) {  // whole warp, in both CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160, 1)
+k_debug_cg2(const float *__restrict__ P, const float *__restrict__ Q, int nrep, int bswap, int ts, float *__restrict__ out, long long *__restrict__ cyc) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *p_s = smem, *q_s = smem + 65536;  // A: 2 K blocks x (hi 16K | lo 16K); B: 2 K blocks x (hi 8K | lo 8K)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 98304);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + 98304 + 64);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (warp == 4) {
+        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+        __syncwarp();
+        tmem_alloc2(tmem_ptr, 256);
+    } else {
+        const uint32_t row = threadIdx.x;
+        for (uint32_t k = 0; k < 128; k += 2) {
+            uint32_t hi, lo;
+            const uint32_t off = (k >> 6) * 32768u + sw128_offset(row, k & 63u);
+            split_pack2(P[(128u * rank + row) * 128 + k], P[(128u * rank + row) * 128 + k + 1], hi, lo);
+            *reinterpret_cast<uint32_t *>(p_s + off) = hi;
+            *reinterpret_cast<uint32_t *>(p_s + off + 16384u) = lo;
+            if (row < 64) {
+                const uint32_t qrow = 64u * (rank ^ (uint32_t)bswap) + row;
+                const uint32_t qoff = (k >> 6) * 16384u + sw128_offset(row, k & 63u);
+                split_pack2(Q[qrow * 128 + k], Q[qrow * 128 + k + 1], hi, lo);
+                *reinterpret_cast<uint32_t *>(q_s + qoff) = hi;
+                *reinterpret_cast<uint32_t *>(q_s + qoff + 8192u) = lo;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *tmem_ptr;
+    if (ts && warp < 4) {  // A operand into TMEM: columns 128..191 hi, 192..255 lo (packed pairs: column c holds K elements 2c, 2c+1)
+        const uint32_t row = threadIdx.x, lane_base = (uint32_t)(warp * 32) << 16;
+        for (uint32_t c0 = 0; c0 < 64; c0 += 8) {
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t k = 2 * (c0 + i);
+                split_pack2(P[(128u * rank + row) * 128 + k], P[(128u * rank + row) * 128 + k + 1], ph[i], pl[i]);
+            }
+            tmem_st8(tbase + lane_base + 128 + c0, ph);
+            tmem_st8(tbase + lane_base + 192 + c0, pl);
+        }
+        tmem_st_wait();
+    }
+    fence_before_sync();
+    cluster_sync_all();
+    fence_after_sync();
+    if (rank == 0 && warp == 4 && lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(256, 128);
+        const uint32_t pa = smem_u32(p_s), qa = smem_u32(q_s);
+        const long long t0 = clock64();
+        uint32_t acc = 0;
+        for (int rep = 0; rep < nrep; ++rep) {
+            for (int term = 0; term < 3; ++term) {  // (P_hi,Q_hi) (P_lo,Q_hi) (P_hi,Q_lo)
+                const uint32_t po = term == 1 ? 16384u : 0u, qo = term == 2 ? 8192u : 0u;
+                for (uint32_t j = 0; j < 8; ++j) {  // 8 k-steps of 16
+                    const uint64_t db = make_desc_sw128(qa + qo + (j >> 2) * 16384u + (j & 3u) * 32u);
+                    if (ts) {
+                        mma2_ts(tbase, tbase + (term == 1 ? 192u : 128u) + j * 8u, db, idesc, acc);
+                    } else {
+                        const uint64_t da = make_desc_sw128(pa + po + (j >> 2) * 32768u + (j & 3u) * 32u);
+                        mma2_ss(tbase, da, db, idesc, acc);
+                    }
+                    acc = 1;
+                }
+            }
+        }
+        const long long t1 = clock64();
+        mma2_commit_mc(&bars[0], (uint16_t)3);
+        mbar_wait(&bars[0], 0);
+        const long long t2 = clock64();
+        cyc[0] = t1 - t0; cyc[1] = t2 - t0;
+    }
+    if (warp < 4) {
+        mbar_wait(&bars[0], 0);
+        fence_after_sync();
+        const uint32_t row = threadIdx.x;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (uint32_t ch = 0; ch < 4; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(tbase + lane_base + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) out[(128u * rank + row) * 128 + ch * 32 + i] = __uint_as_float(r[i]);
+        }
+    }
+    fence_before_sync();
+    cluster_sync_all();
+    if (warp == 4) tmem_dealloc2(tbase, 256);
+}
+}  // namespace tn
+
+// test hook: d_P f32[256,128], d_Q f32[128,128], d_out f32[256,128]; h_cyc = {issue cycles, issue + completion} of nrep x 24 MMAs
+extern "C" int tn_debug_cg2(int device, int nrep, int bswap, int ts, const float *d_P, const float *d_Q, float *d_out, long long *h_cyc) {
+    tn::DeviceGuard g(device);
+    const int smem = 98304 + 128;
+    long long *d_cyc = nullptr;
+    TN_CUDA(cudaMalloc((void **)&d_cyc, 16));
+    TN_CUDA(cudaMemset(d_cyc, 0, 16));
+    TN_CUDA(cudaFuncSetAttribute(tn::k_debug_cg2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tn::k_debug_cg2<<<2, 160, smem>>>(d_P, d_Q, nrep, bswap, ts, d_out, d_cyc);
+    TN_CUDA(cudaGetLastError());
+    TN_CUDA(cudaDeviceSynchronize());
+    TN_CUDA(cudaMemcpy(h_cyc, d_cyc, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d_cyc);
+    return TN_OK;
+}
+
 // test hook: d_P, d_Q f32[128,128], d_out f32[128,128] (first N columns written); lbo / sbo / kstep in bytes describe the
 // MN-major operands (the backward kernel uses lbo = 32768 (next 64-column block), sbo = 1024 (next 8 rows), kstep = 2048)
 extern "C" int tn_debug_gemm_modes(int device, int mode, uint32_t N, uint32_t lbo, uint32_t sbo, uint32_t kstep, const float *d_P,
