@@ -239,6 +239,9 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer-store gather (default) or NCCL all_gather")
     ap.add_argument("--points", type=int, default=None, help="--mode train: points of the Delaunay mesh (default 300000 -> ~2.0 M tetrahedra)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mlp-precision", default="f16w2", choices=["f16w2", "bf16x3"],
+                    help="operand precision of the inference MLP (tn_render_set_mlp_precision): f16w2 = fp16 activations x fp16 hi/lo weights, "
+                         "2 MMAs per product, ~2.6e-5 abs on unit-scale density/colour (library default); bf16x3 = 3 MMAs, ~5e-7")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.rays is None:
@@ -277,6 +280,7 @@ def main():
     model = model.to(dev).eval()
     tracer = model.get_tetrahedra_tracer()
     fr = model._fused_renderer()
+    fr.set_mlp_precision(2 if args.mlp_precision == "f16w2" else 3)
     st = RenderSettings(512, w["num_samples"], w["num_fine_samples"], w["use_biased_sampler"], float(model.collider.far_plane), (1.0, 1.0, 1.0))
     nsteps = args.warmup + args.steps
     # a different ray batch every step; each rank gets its own shard (weak scaling)
@@ -349,6 +353,11 @@ def main():
     ms_total, _, launches = timed(False)
     ms_e2e, _, _ = timed(True)
     _, kern_ms, _ = timed(False, profile=True)  # same steps again with CUDA events around every kernel of the library
+    # the same timed region with the other operand precision of the MLP (reported beside the headline, never as `value`)
+    other = "bf16x3" if args.mlp_precision == "f16w2" else "f16w2"
+    fr.set_mlp_precision(3 if other == "bf16x3" else 2)
+    ms_other, _, _ = timed(False)
+    fr.set_mlp_precision(2 if args.mlp_precision == "f16w2" else 3)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     tracer.synchronize()
@@ -387,8 +396,9 @@ def main():
         if dom in flops:
             ach = flops[dom] / (kern_ms[dom] * 1e-3) / 1e12
             roof.update(achieved=ach, frac=ach / pk["bf16_tflops"],
-                        note="algorithmic fp32-equivalent FLOPs (SURVEY §8d); the kernel issues 3 bf16 MMAs per algorithmic MAC (bf16x3), "
-                             "so tensor-pipe occupancy is ~3x this fraction")
+                        note="algorithmic fp32-equivalent FLOPs (SURVEY §8d); the kernel issues "
+                             + ("2 fp16 MMAs per algorithmic MAC (f16w2), so tensor-pipe occupancy is ~2x this fraction" if args.mlp_precision == "f16w2"
+                                else "3 bf16 MMAs per algorithmic MAC (bf16x3), so tensor-pipe occupancy is ~3x this fraction"))
         # the traversal (BASELINE metric: "traversal HBM% of roofline"): SURVEY §8d algorithmic bytes / (prefetch + trace time)
         Fcount = tracer.num_faces()
         tb = 28 * R + 52 * sum_k + 12 * len(V) + 16 * len(C) + 20 * Fcount
@@ -403,8 +413,12 @@ def main():
         line = {
             "metric": "rays/sec (4096-ray batch, 300k-tet mesh)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (trace/interp/compositing) + bf16x3 tensor-core MLP with f32 accumulate", "data": "synthetic",
+            "dtype": "f32 (trace/interp/compositing) + " + ("f16w2 tensor-core MLP (fp16 activations x fp16 hi/lo weights, f32 accumulate; per-sample "
+                                                           "density/colour within 1e-4 of the fp32 oracle, tests/test_gpu_render.py)" if args.mlp_precision == "f16w2"
+                                                           else "bf16x3 tensor-core MLP with f32 accumulate"), "data": "synthetic",
             "config": workload_config(args.workload, "eval", R, world, len(C)),
+            "mlp_precision": {"mode": args.mlp_precision, "other_mode": other, "other_mode_ms_per_step": ms_other / args.steps,
+                              "other_mode_value": total_rays / (ms_other * 1e-3)},
             "timing": {"l2": "flushed between timed steps (256 MiB fill); a new ray batch every step", "events": "CUDA events per step on the launch stream, max over ranks",
                        "gather": {"none": "single GPU", "peer": "fused: render kernels store pixels into every rank's gathered buffer over NVLink (no collective)",
                                   "nccl": "NCCL all_gather_into_tensor inside every step"}[gather_mode]},

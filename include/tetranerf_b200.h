@@ -105,6 +105,11 @@ typedef struct tn_render_config {
 
 /* field: f32[64,V] feature-major.  Keeps a [V,64] row-major shadow inside the tracer. */
 int tn_render_set_field(tn_tracer *h, const float *d_field, uint32_t C, uint32_t V, void *stream);
+/* operand precision of the inference MLP (tn_render; the training forward always uses 3):
+ *   3 = "bf16x3": a*w = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in bf16 halves, 3 MMAs per K step, ~5e-7 absolute on unit-scale outputs;
+ *   2 = "f16w2":  fp16 activations, fp16 hi/lo weights, 2 MMAs per K step, ~2.6e-5 absolute (inside the 1e-4 per-sample bar).
+ * Initial value: environment variable TETRANERF_B200_MLP_PREC, else 2. */
+int tn_render_set_mlp_precision(tn_tracer *h, int prec);
 /* mlp_base.layers.{0,1,2}.{weight,bias}, mlp_head.layers.0.{weight,bias}, field_output_color.net.*,
  * field_output_density.net.* as 12 device pointers in that order (torch nn.Linear [out,in] layout). */
 int tn_render_set_weights(tn_tracer *h, const float *const *d_params12, void *stream);

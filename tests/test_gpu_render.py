@@ -22,7 +22,7 @@ def _from_ptr(ptr, shape, dtype):
     return t
 
 
-def setup(V, C, field_kind="normal"):
+def setup(V, C, field_kind="normal", prec=3):
     from tetranerf import cpp
     from tetranerf.b200.render import FusedRenderer
 
@@ -33,16 +33,20 @@ def setup(V, C, field_kind="normal"):
     fr = FusedRenderer(tr)
     fr.set_field(torch.from_numpy(field).to(DEV))
     fr.set_weights(params)
+    fr.set_mlp_precision(prec)
     return tr, fr, field, params
 
 
+# prec: operand precision of the tensor-core MLP -- 3 = bf16x3 (fp32-level), 2 = f16w2 (fp16 activations x fp16 hi/lo weights, 2 MMAs per
+# product).  BOTH are held to the same bars: the north-star tolerance of 1e-4 absolute per sample and per pixel.
+@pytest.mark.parametrize("prec", [3, 2])
 @pytest.mark.parametrize("cfgname", ["tetra_nerf", "tetra_nerf_original", "small_uniform", "small_biased"])
 @pytest.mark.parametrize("field_kind", ["normal", "init"])
-def test_fused_render_vs_oracle(small_mesh, cfgname, field_kind):
+def test_fused_render_vs_oracle(small_mesh, cfgname, field_kind, prec):
     from tetranerf.b200.render import RenderSettings
 
     V, C = small_mesh
-    tr, fr, field, params = setup(V, C, field_kind)
+    tr, fr, field, params = setup(V, C, field_kind, prec)
     o, d = syn.camera_rays(300)
     o[5] = [5, 5, 5]; d[5] = [1, 0, 0]       # empty ray
     o[17] = [0.5, 0.5, 0.5]                   # origin inside the mesh
@@ -77,7 +81,7 @@ def test_fused_render_vs_oracle(small_mesh, cfgname, field_kind):
     torch.testing.assert_close(eb_c, aux["coarse_euclid"][order], rtol=2e-6, atol=2e-6)
     dens = _from_ptr(bufs["dens_c"], (n_act, Sc), torch.float32).cpu()
     dref = aux["coarse_density"][order][..., 0]
-    print(cfgname, field_kind, "coarse density max abs err", (dens - dref).abs().max().item())
+    print(cfgname, field_kind, f"prec={prec}", "coarse density max abs err", (dens - dref).abs().max().item())
     assert (dens - dref).abs().max().item() < 1e-4
     eb_f = _from_ptr(bufs["ebins_f"], (n_act, S2 + 1), torch.float32).cpu()
     print("fine bins max abs err", (eb_f - aux["fine_euclid"][order]).abs().max().item())
@@ -103,19 +107,20 @@ def test_fused_render_vs_oracle(small_mesh, cfgname, field_kind):
     e_rgb = (out["rgb"].cpu() - ref["rgb"]).abs().max().item()
     e_acc = (out["accumulation"].cpu() - ref["accumulation"]).abs().max().item()
     e_dep = (out["depth"].cpu() - ref["depth"]).abs()
-    print(f"{cfgname}/{field_kind}: max|rgb| {e_rgb:.2e}  max|acc| {e_acc:.2e}  depth: max {e_dep.max().item():.2e} median {e_dep.median().item():.2e}")
+    print(f"{cfgname}/{field_kind}/prec={prec}: max|rgb| {e_rgb:.2e}  max|acc| {e_acc:.2e}  depth: max {e_dep.max().item():.2e} median {e_dep.median().item():.2e}")
     assert e_rgb < 1e-4 and e_acc < 1e-4
     # median depth is a step function of the cumulative weights: allow a handful of rays to pick the neighbouring sample
     assert (e_dep.flatten() > 1e-4).sum().item() <= max(2, len(o) // 100)
 
 
+@pytest.mark.parametrize("prec", [3, 2])
 @pytest.mark.parametrize("biased", [False, True])
-def test_fused_render_single_pass(small_mesh, biased):
+def test_fused_render_single_pass(small_mesh, biased, prec):
     """num_fine_samples == 0 (model.py:573: the PDF pass is skipped, colours come from the first pass)"""
     from tetranerf.b200.render import RenderSettings
 
     V, C = small_mesh
-    tr, fr, field, params = setup(V, C)
+    tr, fr, field, params = setup(V, C, prec=prec)
     o, d = syn.camera_rays(200, seed=9)
     o[7] = [5, 5, 5]; d[7] = [1, 0, 0]
     st = RenderSettings(num_samples=96, num_fine_samples=0, use_biased_sampler=biased)

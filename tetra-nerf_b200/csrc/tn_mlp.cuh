@@ -45,12 +45,20 @@ constexpr uint32_t MLP_REGS_WORKER = 88, MLP_REGS_CTRL = 40, MLP_REGS_GATHER = 8
 static_assert(512 * MLP_REGS_WORKER + 128 * MLP_REGS_CTRL + 128 * MLP_REGS_GATHER <= MLP_THREADS * 80, "register budget exceeds the launch allocation: setmaxnreg.inc would block forever");
 constexpr uint32_t MLP_TL_CAP = 96;                        // debug timeline records buffered in shared memory
 constexpr uint32_t MLP_W_RESIDENT = 163840;                // L1 32K + L2 64K + L3 64K
-constexpr uint32_t MLP_RING_STAGES = 2, MLP_RING_CHUNK = 16384;
+constexpr uint32_t MLP_RING_STAGES = 2, MLP_RING_CHUNK = 16384;   // (stages of the bf16x3 mode; the f16w2 mode has three, see mlp_ring_stages)
+// Operand precision of the tensor-core products (template parameter PREC of k_mlp):
+//   3 = "bf16x3": a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, bf16 halves, 3 MMAs per K step -- 5e-7 absolute on density / colour of
+//       unit scale, the training forward and the reference mode;
+//   2 = "f16w2": the activations are ONE fp16 value (11-bit significand), the weights an fp16 hi/lo pair: a*w ~= a*(w_hi + w_lo),
+//       2 MMAs per K step, no A_lo operand (half the epilogue's conversion work and TMEM stores, a 16 KB layer-0 operand, and the
+//       freed 16 KB become a third stage of the layer-4 weight ring).  Error ~2^-12 relative per activation: 2.6e-5 absolute on
+//       density / colour of unit scale (tools/split_accuracy.py), inside the 1e-4 per-sample bar.
+__host__ __device__ constexpr uint32_t mlp_ring_stages(int prec) { return prec == 2 ? 3u : 2u; }
 constexpr uint32_t MLP_OFF_RING = MLP_W_RESIDENT;                                // 2 x 16K
 constexpr uint32_t MLP_OFF_A0 = MLP_OFF_RING + MLP_RING_STAGES * MLP_RING_CHUNK; // layer-0 A operand: hi 16K | lo 16K
 constexpr uint32_t MLP_OFF_HEAD = MLP_OFF_A0 + 32768;                            // wd[128] wc[3][128] bd bc[3] (+pad)
 constexpr uint32_t MLP_OFF_BARS = MLP_OFF_HEAD + 520 * 4;
-constexpr uint32_t MLP_OFF_TL = MLP_OFF_BARS + 144;  // debug timeline: counter, enable flag, MLP_TL_CAP records
+constexpr uint32_t MLP_OFF_TL = MLP_OFF_BARS + 160;  // debug timeline: counter, enable flag, MLP_TL_CAP records
 // (the hidden-layer biases are read through L1 and the head partial sums are exchanged through TMEM: with 160 KB of
 //  resident weights, the 32 KB ring and the 32 KB layer-0 operand there is no shared memory left for them)
 constexpr uint32_t MLP_SMEM_BYTES = MLP_OFF_TL + 8 * (MLP_TL_CAP + 2);
@@ -117,7 +125,7 @@ __device__ __forceinline__ void split2(float2 r, uint32_t &hi, uint32_t &lo) {
 // The bias of the first 16 columns is loaded by the caller BEFORE it waits for the accumulator (bpre), and every bias register is
 // refilled with the next chunk's value as soon as it has been consumed: the loads (L1 / L2, SM-dependent latency) never sit between
 // the TMEM load and the first add any more.
-template <int KIND>
+template <int KIND, int PREC>
 __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint32_t alo, uint32_t h, const float *__restrict__ bias128, float2 (&bpre)[8],
                                                bool dens, const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc) {
     using namespace tc;
@@ -140,7 +148,7 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
             float2 x = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b);
             x.x = fmaxf(x.x, 0.f);
             x.y = fmaxf(x.y, 0.f);
-            if (KIND == 0) split2(x, ph[i], pl[i]);
+            if (KIND == 0) { if (PREC == 2) ph[i] = tc::pack2_f16(x.x, x.y); else split2(x, ph[i], pl[i]); }
             if (KIND == 2 || (KIND == 0 && dens)) dsum = fma2(x, *reinterpret_cast<const float2 *>(wd + col0 + 2 * i), dsum);
             if (KIND == 3) {
                 c0 = fma2(x, *reinterpret_cast<const float2 *>(wc + col0 + 2 * i), c0);
@@ -150,7 +158,7 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
         }
         if (KIND == 0) {
             tmem_st8(ahi + (col0 >> 1), ph);
-            tmem_st8(alo + (col0 >> 1), pl);
+            if (PREC != 2) tmem_st8(alo + (col0 >> 1), pl);
         }
     }
     if (KIND == 2 || (KIND == 0 && dens)) acc.x = dsum.x + dsum.y;
@@ -192,24 +200,26 @@ struct MlpIssue {
     uint32_t rst, rpar;    // ring stage / parity
     uint32_t nseq, done;   // sequence number of the CTA's next tile; set once the tile scheduler has run dry
 };
-constexpr uint32_t MLP_BAR_A_READY = 0, MLP_BAR_D_READY = 2, MLP_BAR_W = 4, MLP_BAR_RING_FULL = 5, MLP_BAR_RING_EMPTY = 7, MLP_BAR_A0_FULL = 9,
-                   MLP_BAR_A0_EMPTY = 11;
-constexpr uint32_t MLP_TILE_IDS_OFF = 112;        // byte offset of tile_ids[8] inside the barrier block (after 13 barriers + tmem ptr + stop flag)
+constexpr uint32_t MLP_BAR_A_READY = 0, MLP_BAR_D_READY = 2, MLP_BAR_W = 4, MLP_BAR_RING_FULL = 5, MLP_BAR_RING_EMPTY = 8, MLP_BAR_A0_FULL = 11,
+                   MLP_BAR_A0_EMPTY = 13;
+constexpr uint32_t MLP_TILE_IDS_OFF = 128;        // byte offset of tile_ids[8] inside the barrier block (after 15 barriers + tmem ptr + stop flag)
 constexpr uint32_t MLP_NO_TILE = 0xFFFFFFFFu;     // sentinel: the scheduler has run dry
 
 // 12 MMAs of one 64-wide K block KB with A in TMEM: (A_hi,W_hi) (A_lo,W_hi) (A_hi,W_lo).  a = TMEM address of A_hi
 // (A_lo is 64 columns further); WH / WL = low-descriptor-word offsets of the hi / lo weight blocks in the resident image
-template <bool FIRST, uint32_t KB, uint32_t WH, uint32_t WL>
+template <bool FIRST, uint32_t KB, uint32_t WH, uint32_t WL, int PREC>
 __device__ __forceinline__ void kblock_ts(uint32_t d_t, uint32_t a, uint32_t dw, uint32_t idesc) {
     using namespace tc;
     mma_ts_o<!FIRST, KB * 32u + 0u, WH + 0u>(d_t, a, dw, idesc);
     mma_ts_o<true, KB * 32u + 8u, WH + 2u>(d_t, a, dw, idesc);
     mma_ts_o<true, KB * 32u + 16u, WH + 4u>(d_t, a, dw, idesc);
     mma_ts_o<true, KB * 32u + 24u, WH + 6u>(d_t, a, dw, idesc);
-    mma_ts_o<true, 64u + KB * 32u + 0u, WH + 0u>(d_t, a, dw, idesc);
-    mma_ts_o<true, 64u + KB * 32u + 8u, WH + 2u>(d_t, a, dw, idesc);
-    mma_ts_o<true, 64u + KB * 32u + 16u, WH + 4u>(d_t, a, dw, idesc);
-    mma_ts_o<true, 64u + KB * 32u + 24u, WH + 6u>(d_t, a, dw, idesc);
+    if (PREC != 2) {  // (A_lo, W_hi)
+        mma_ts_o<true, 64u + KB * 32u + 0u, WH + 0u>(d_t, a, dw, idesc);
+        mma_ts_o<true, 64u + KB * 32u + 8u, WH + 2u>(d_t, a, dw, idesc);
+        mma_ts_o<true, 64u + KB * 32u + 16u, WH + 4u>(d_t, a, dw, idesc);
+        mma_ts_o<true, 64u + KB * 32u + 24u, WH + 6u>(d_t, a, dw, idesc);
+    }
     mma_ts_o<true, KB * 32u + 0u, WL + 0u>(d_t, a, dw, idesc);
     mma_ts_o<true, KB * 32u + 8u, WL + 2u>(d_t, a, dw, idesc);
     mma_ts_o<true, KB * 32u + 16u, WL + 4u>(d_t, a, dw, idesc);
@@ -217,7 +227,7 @@ __device__ __forceinline__ void kblock_ts(uint32_t d_t, uint32_t a, uint32_t dw,
 }
 
 // one ring chunk of layer 4: BLK 0: hi kb0, 1: lo kb0, 2: hi kb1, 3: lo kb1 (128 output rows x 64 K); hi blocks take A_hi and A_lo
-template <int BLK>
+template <int BLK, int PREC>
 __device__ __forceinline__ void ring_chunk(uint32_t d_t, uint32_t a, uint32_t b, uint32_t idesc) {
     using namespace tc;
     constexpr uint32_t KB = (uint32_t)(BLK >> 1) * 32u;
@@ -225,7 +235,7 @@ __device__ __forceinline__ void ring_chunk(uint32_t d_t, uint32_t a, uint32_t b,
     mma_ts_o<true, KB + 8u, 2u>(d_t, a, b, idesc);
     mma_ts_o<true, KB + 16u, 4u>(d_t, a, b, idesc);
     mma_ts_o<true, KB + 24u, 6u>(d_t, a, b, idesc);
-    if ((BLK & 1) == 0) {
+    if ((BLK & 1) == 0 && PREC != 2) {
         mma_ts_o<true, 64u + KB + 0u, 0u>(d_t, a, b, idesc);
         mma_ts_o<true, 64u + KB + 8u, 2u>(d_t, a, b, idesc);
         mma_ts_o<true, 64u + KB + 16u, 4u>(d_t, a, b, idesc);
@@ -234,12 +244,12 @@ __device__ __forceinline__ void ring_chunk(uint32_t d_t, uint32_t a, uint32_t b,
 }
 
 // one layer of one slot; returns false when the slot has no further tile (its workers have been released)
-template <bool FINE, int SLOT>
+template <bool FINE, int SLOT, int PREC>
 __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &layer, const MlpParams &p) {
     using namespace tc;
     constexpr uint32_t L = FINE ? 4 : 3;
     constexpr uint32_t NBUF = FINE ? 1 : 2;
-    constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    constexpr uint32_t idesc = PREC == 2 ? make_idesc_f16(128, 128) : make_idesc_bf16(128, 128);
     mbar_wait_a(s.bars + 8u * (MLP_BAR_A_READY + SLOT), par);
     par ^= 1u;
     const uint32_t l = layer;
@@ -267,10 +277,12 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         mma_ss_o<true, 2u, 2u>(d_t, da, s.dw, idesc);
         mma_ss_o<true, 4u, 4u>(d_t, da, s.dw, idesc);
         mma_ss_o<true, 6u, 6u>(d_t, da, s.dw, idesc);
-        mma_ss_o<true, 1024u + 0u, 0u>(d_t, da, s.dw, idesc);
-        mma_ss_o<true, 1024u + 2u, 2u>(d_t, da, s.dw, idesc);
-        mma_ss_o<true, 1024u + 4u, 4u>(d_t, da, s.dw, idesc);
-        mma_ss_o<true, 1024u + 6u, 6u>(d_t, da, s.dw, idesc);
+        if (PREC != 2) {  // (A0_lo, W_hi): the lo block of the operand is 16 KB further
+            mma_ss_o<true, 1024u + 0u, 0u>(d_t, da, s.dw, idesc);
+            mma_ss_o<true, 1024u + 2u, 2u>(d_t, da, s.dw, idesc);
+            mma_ss_o<true, 1024u + 4u, 4u>(d_t, da, s.dw, idesc);
+            mma_ss_o<true, 1024u + 6u, 6u>(d_t, da, s.dw, idesc);
+        }
         mma_ss_o<true, 0u, 1024u + 0u>(d_t, da, s.dw, idesc);
         mma_ss_o<true, 2u, 1024u + 2u>(d_t, da, s.dw, idesc);
         mma_ss_o<true, 4u, 1024u + 4u>(d_t, da, s.dw, idesc);
@@ -280,19 +292,19 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
         fence_after_sync();
         tl_mark(p.timeline, 0, 17, 1 + SLOT, 0, l);
         if (l == 1) {
-            kblock_ts<true, 0u, 2048u, 3072u>(d_t, a, s.dw, idesc);
-            kblock_ts<false, 1u, 4096u, 5120u>(d_t, a, s.dw, idesc);
+            kblock_ts<true, 0u, 2048u, 3072u, PREC>(d_t, a, s.dw, idesc);
+            kblock_ts<false, 1u, 4096u, 5120u, PREC>(d_t, a, s.dw, idesc);
         } else if (l == 2) {
-            kblock_ts<true, 0u, 6144u, 7168u>(d_t, a, s.dw, idesc);
-            kblock_ts<false, 1u, 8192u, 9216u>(d_t, a, s.dw, idesc);
+            kblock_ts<true, 0u, 6144u, 7168u, PREC>(d_t, a, s.dw, idesc);
+            kblock_ts<false, 1u, 8192u, 9216u, PREC>(d_t, a, s.dw, idesc);
         } else {
             // layer 4: the chunks hi(kb0) lo(kb0) hi(kb1) lo(kb1) stream through the ring
 #define TN_RING_CHUNK(J)                                                                              \
     {                                                                                                 \
         mbar_wait_a(s.bars + 8u * (MLP_BAR_RING_FULL + s.rst), s.rpar);                               \
-        ring_chunk<(J)>(d_t, a, s.dr + s.rst * (MLP_RING_CHUNK >> 4), idesc);                         \
+        ring_chunk<(J), PREC>(d_t, a, s.dr + s.rst * (MLP_RING_CHUNK >> 4), idesc);                   \
         mma_commit_a(s.bars + 8u * (MLP_BAR_RING_EMPTY + s.rst));                                     \
-        if (++s.rst == MLP_RING_STAGES) { s.rst = 0; s.rpar ^= 1u; }                                  \
+        if (++s.rst == mlp_ring_stages(PREC)) { s.rst = 0; s.rpar ^= 1u; }                            \
     }
             TN_RING_CHUNK(0) TN_RING_CHUNK(1) TN_RING_CHUNK(2) TN_RING_CHUNK(3)
 #undef TN_RING_CHUNK
@@ -303,8 +315,10 @@ __device__ __forceinline__ bool mlp_serve(MlpIssue &s, uint32_t &par, uint32_t &
     return true;
 }
 
-template <bool FINE>
+template <bool FINE, int PREC>
 __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
+    constexpr uint32_t RS = mlp_ring_stages(PREC);
+    constexpr uint32_t A0_OFF = MLP_OFF_A0 + (PREC == 2 ? 16384u : 0u);  // f16w2: the first 16 KB of the operand area are ring stage 2
     using namespace tc;
     uint8_t *smem = tn_mlp_smem;
     uint8_t *w_s = smem;
@@ -314,11 +328,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
     uint64_t *a_ready = bars + MLP_BAR_A_READY;        // [2] count 8: the slot's warps are done with D / have written the next A
     uint64_t *d_ready = bars + MLP_BAR_D_READY;        // [2] count 1 (tcgen05.commit; plain arrive when the slot is retired)
     uint64_t *w_bar = bars + MLP_BAR_W;                // resident weights landed
-    uint64_t *ring_full = bars + MLP_BAR_RING_FULL;    // [2]
-    uint64_t *ring_empty = bars + MLP_BAR_RING_EMPTY;  // [2]
+    uint64_t *ring_full = bars + MLP_BAR_RING_FULL;    // [3]
+    uint64_t *ring_empty = bars + MLP_BAR_RING_EMPTY;  // [3]
     uint64_t *a0_full = bars + MLP_BAR_A0_FULL;        // [2] count 4: every gather warp has stored its rows of the layer-0 operand
     uint64_t *a0_empty = bars + MLP_BAR_A0_EMPTY;      // [2] count 1 (tcgen05.commit after the layer-0 MMAs)
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 13);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 15);
     volatile uint32_t *stop_flag = tmem_ptr + 1;       // set by the issuer when both slots are retired (stops the ring producer)
     volatile uint32_t *tile_ids = reinterpret_cast<volatile uint32_t *>(smem + MLP_OFF_BARS + MLP_TILE_IDS_OFF);  // [8] tile of sequence number n at n & 7
 
@@ -337,10 +351,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
             mbar_init(&a_ready[0], 8); mbar_init(&a_ready[1], 8);
             mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
             mbar_init(w_bar, 1);
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1);
-                mbar_init(&a0_full[i], MLP_GATHER_WARPS); mbar_init(&a0_empty[i], 1);
-            }
+            for (int i = 0; i < 3; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&a0_full[i], MLP_GATHER_WARPS); mbar_init(&a0_empty[i], 1); }
             fence_barrier_init();
             *stop_flag = 0u;
             tile_ids[0] = has_work ? blockIdx.x : MLP_NO_TILE;
@@ -385,11 +397,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
                         if (stop) break;
                         mbar_arrive_expect_tx(&ring_full[st], MLP_RING_CHUNK);
                         tma_bulk_g2s(ring_s + st * MLP_RING_CHUNK, w4 + (i & 3u) * MLP_RING_CHUNK, MLP_RING_CHUNK, &ring_full[st]);
-                        if (++st == MLP_RING_STAGES) { st = 0; par ^= 1u; }
+                        if (++st == RS) { st = 0; par ^= 1u; }
                     }
-                    const uint32_t fills0 = (i + 1u) / 2u, fills1 = i / 2u;  // fills of stage 0 / 1; phase f of ring_full = fill f
-                    if (fills0) mbar_wait_backoff(&ring_full[0], (fills0 - 1u) & 1u, 64);
-                    if (fills1) mbar_wait_backoff(&ring_full[1], (fills1 - 1u) & 1u, 64);
+                    for (uint32_t q = 0; q < RS; ++q) {  // fills of stage q among chunks 0..i-1; phase f of ring_full = fill f
+                        const uint32_t fills = (i + RS - 1u - q) / RS;
+                        if (fills) mbar_wait_backoff(&ring_full[q], (fills - 1u) & 1u, 64);
+                    }
                 }
             }
         } else if (warp == 17) {
@@ -400,16 +413,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
                 s.bars = smem_u32(bars);
                 s.dw = desc_lo(smem_u32(w_s));
                 s.dr = desc_lo(smem_u32(ring_s));
-                s.da0 = desc_lo(smem_u32(smem + MLP_OFF_A0));
+                s.da0 = desc_lo(smem_u32(smem + A0_OFF));
                 s.rst = 0; s.rpar = 0; s.nseq = 0; s.done = 0;
                 uint32_t par0 = 0, par1 = 0, layer0 = 0, layer1 = 0;
                 mbar_wait(w_bar, 0);
                 // strict alternation between the slots; slot 1 starts one round late so that the layer-0 passes (the consumers
                 // of the layer-0 operand buffer) are evenly spaced and each slot's epilogue runs under the other slot's MMAs
-                bool alive0 = mlp_serve<FINE, 0>(s, par0, layer0, p), alive1 = true;
+                bool alive0 = mlp_serve<FINE, 0, PREC>(s, par0, layer0, p), alive1 = true;
                 while (alive0 | alive1) {
-                    if (alive0) alive0 = mlp_serve<FINE, 0>(s, par0, layer0, p);
-                    if (alive1) alive1 = mlp_serve<FINE, 1>(s, par1, layer1, p);
+                    if (alive0) alive0 = mlp_serve<FINE, 0, PREC>(s, par0, layer0, p);
+                    if (alive1) alive1 = mlp_serve<FINE, 1, PREC>(s, par1, layer1, p);
                 }
                 *stop_flag = 1u;
             }
@@ -472,7 +485,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
             nxt = tile_ids[(n + 1u) & 7u];
             TN_LOAD_IDS(nxt, nv, nb0, nb1, nb2)
             const uint32_t b = NBUF == 2 ? (n & 1u) : 0u;
-            const uint32_t a0 = smem_u32(smem + (b ? MLP_OFF_RING : MLP_OFF_A0));
+            const uint32_t a0 = smem_u32(smem + (b ? MLP_OFF_RING : A0_OFF));
 #if TN_MLP_STATS
             if (p.timeline != nullptr) dbg_t = clock64();
 #endif
@@ -497,14 +510,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
                         o.x = __fmaf_rn(b1, fc[2].x, o.x); o.y = __fmaf_rn(b1, fc[2].y, o.y); o.z = __fmaf_rn(b1, fc[2].z, o.z); o.w = __fmaf_rn(b1, fc[2].w, o.w);
                         o.x = __fmaf_rn(b2, fc[3].x, o.x); o.y = __fmaf_rn(b2, fc[3].y, o.y); o.z = __fmaf_rn(b2, fc[3].z, o.z); o.w = __fmaf_rn(b2, fc[3].w, o.w);
                         o.x = __fmaf_rn(w0, fc[0].x, o.x); o.y = __fmaf_rn(w0, fc[0].y, o.y); o.z = __fmaf_rn(w0, fc[0].z, o.z); o.w = __fmaf_rn(w0, fc[0].w, o.w);
-                        uint32_t h0, l0, h1, l1;
-                        split_pack2(o.x, o.y, h0, l0);
-                        split_pack2(o.z, o.w, h1, l1);
+                        uint32_t h0, l0 = 0, h1, l1 = 0;
+                        if (PREC == 2) { h0 = pack2_f16(o.x, o.y); h1 = pack2_f16(o.z, o.w); }
+                        else { split_pack2(o.x, o.y, h0, l0); split_pack2(o.z, o.w, h1, l1); }
                         // tile row R = 32 g + 2 c + hw inside the swizzled [128][64] bf16 block
                         const uint32_t R = g * 32u + (uint32_t)r, r7 = R & 7u;
                         const uint32_t addr = a0 + (R >> 3) * 1024u + r7 * 128u + (((l16 >> 1) ^ r7) << 4) + (l16 & 1u) * 8u;
                         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(h0), "r"(h1) : "memory");
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + 16384u), "r"(l0), "r"(l1) : "memory");
+                        if (PREC != 2) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + 16384u), "r"(l0), "r"(l1) : "memory");
                     }
                     // refill the two pipeline buffers just consumed: 4 steps ahead, running into the next tile at the end of this one
                     if (cc + 4 < 16) { TN_ISSUE(cc & 3, cv, cc + 4) TN_ISSUE((cc + 1) & 3, cv, cc + 5) }
@@ -570,13 +583,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
                     if (FINE) bias4 = p.dirbias + (size_t)(min(my_row, total_rows - 1) / p.S) * 128;  // per-ray direction bias of this thread's row
                 }
                 if (l < L - 1) {
-                    layer_epilogue<0>(d_t, ahi, alo, h, p.bias + l * 128, bpre, FINE && l == 2, wd, wc, acc);
+                    layer_epilogue<0, PREC>(d_t, ahi, alo, h, p.bias + l * 128, bpre, FINE && l == 2, wd, wc, acc);
                     // the next layer's first bias chunk: in flight while the next GEMM runs
                     if (FINE && l == 2) bias_prefetch(bias4, h, bpre); else bias_prefetch(p.bias + (l + 1) * 128, h, bpre);
                 } else if (FINE) {
-                    layer_epilogue<3>(d_t, ahi, alo, h, bias4, bpre, false, wd, wc, acc);
+                    layer_epilogue<3, PREC>(d_t, ahi, alo, h, bias4, bpre, false, wd, wc, acc);
                 } else {
-                    layer_epilogue<2>(d_t, ahi, alo, h, p.bias + 256, bpre, false, wd, wc, acc);
+                    layer_epilogue<2, PREC>(d_t, ahi, alo, h, p.bias + 256, bpre, false, wd, wc, acc);
                 }
                 // next A operand written (l < L-1) / accumulator read out and free for the next tile (l == L-1)
                 if (l < L - 1) tmem_st_wait();

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <vector>
 
+#include <cstdlib>
 #include "tn_common.cuh"
 #include "tn_mlp.cuh"
 #include "tn_mlp_bwd.cuh"
@@ -30,7 +31,9 @@ struct RenderState {
     float *fshadow = nullptr;  // [V,64]
     uint32_t V = 0;
     // weights
-    uint8_t *wimg = nullptr;   // L1 32K | L2 64K | L3 64K | L4(base part) 64K
+    uint8_t *wimg = nullptr;   // L1 32K | L2 64K | L3 64K | L4(base part) 64K  (bf16 hi/lo)
+    uint8_t *wimg16 = nullptr; // the same image with fp16 hi/lo halves (mlp_prec == 2)
+    int mlp_prec = 2;          // operand precision of the inference MLP: 2 = f16w2 (default), 3 = bf16x3 (tn_mlp.cuh); training always runs 3
     float *bias = nullptr;     // b1 b2 b3 [3][128]
     float *head = nullptr;     // wd[128] wc[3][128] bd bc[3]
     float *w4dir = nullptr;    // [128][27] + b4[128]
@@ -79,7 +82,7 @@ void free_render(tn_tracer *h) {
     if (!h->render) return;
     RenderState *r = h->render;
     free_ws(r);
-    cudaFree(r->fshadow); cudaFree(r->wimg); cudaFree(r->bias); cudaFree(r->head); cudaFree(r->w4dir);
+    cudaFree(r->fshadow); cudaFree(r->wimg); cudaFree(r->wimg16); cudaFree(r->bias); cudaFree(r->head); cudaFree(r->w4dir);
     cudaFree(r->wimg_bwd); cudaFree(r->sbins_f); cudaFree(r->enc); cudaFree(r->dout); cudaFree(r->gshadow); cudaFree(r->gw); cudaFree(r->g_dirbias);
     cudaFree(r->scratch);
     for (auto &e : r->ev) if (e) cudaEventDestroy(e);
@@ -89,7 +92,11 @@ void free_render(tn_tracer *h) {
 }
 
 static RenderState *state(tn_tracer *h) {
-    if (!h->render) h->render = new RenderState();
+    if (!h->render) {
+        h->render = new RenderState();
+        const char *e = getenv("TETRANERF_B200_MLP_PREC");  // 2 / 3: initial operand precision of the inference MLP (tn_render_set_mlp_precision)
+        if (e && (atoi(e) == 2 || atoi(e) == 3)) h->render->mlp_prec = atoi(e);
+    }
     return h->render;
 }
 
@@ -653,6 +660,16 @@ extern "C" int tn_render_set_field(tn_tracer *h, const float *d_field, uint32_t 
     return TN_OK;
 }
 
+// operand precision of the inference MLP: 2 = f16w2 (default: fp16 activations, fp16 hi/lo weights; 2.6e-5 absolute on unit-scale
+// density / colour, inside the 1e-4 per-sample bar; ~21 % less MLP time), 3 = bf16x3 (fp32-level).  The training forward always runs 3.
+extern "C" int tn_render_set_mlp_precision(tn_tracer *h, int prec) {
+    if (!h) return fail(TN_ERR_ARG, "null tracer");
+    if (prec != 2 && prec != 3) return fail(TN_ERR_ARG, "tn_render_set_mlp_precision: 2 (f16w2) or 3 (bf16x3)");
+    DeviceGuard g(h->device);
+    state(h)->mlp_prec = prec;
+    return TN_OK;
+}
+
 extern "C" int tn_render_set_weights(tn_tracer *h, const float *const *P, void *stream) {
     if (!h || !P) return fail(TN_ERR_ARG, "null argument");
     DeviceGuard g(h->device);
@@ -660,6 +677,7 @@ extern "C" int tn_render_set_weights(tn_tracer *h, const float *const *P, void *
     cudaStream_t s = (cudaStream_t)stream;
     if (!r->wimg) {
         TN_CUDA(cudaMalloc((void **)&r->wimg, 32768 + 3 * 65536));
+        TN_CUDA(cudaMalloc((void **)&r->wimg16, 32768 + 3 * 65536));
         TN_CUDA(cudaMalloc((void **)&r->bias, sizeof(float) * 384));
         TN_CUDA(cudaMalloc((void **)&r->head, sizeof(float) * 520));
         TN_CUDA(cudaMalloc((void **)&r->w4dir, sizeof(float) * (128 * 27 + 128)));
@@ -668,6 +686,10 @@ extern "C" int tn_render_set_weights(tn_tracer *h, const float *const *P, void *
     launch_pack_weights(P[2], 128, 0, 128, r->wimg + 32768, s);           // mlp_base.layers.1.weight [128,128]
     launch_pack_weights(P[4], 128, 0, 128, r->wimg + 32768 + 65536, s);   // mlp_base.layers.2.weight
     launch_pack_weights(P[6], 155, 27, 128, r->wimg + 32768 + 131072, s); // mlp_head.layers.0.weight [128,155], base part
+    launch_pack_weights(P[0], 64, 0, 64, r->wimg16, s, 32768u, 16384u, 1);
+    launch_pack_weights(P[2], 128, 0, 128, r->wimg16 + 32768, s, 32768u, 16384u, 1);
+    launch_pack_weights(P[4], 128, 0, 128, r->wimg16 + 32768 + 65536, s, 32768u, 16384u, 1);
+    launch_pack_weights(P[6], 155, 27, 128, r->wimg16 + 32768 + 131072, s, 32768u, 16384u, 1);
     k_pack_small<<<1, 128, 0, s>>>(P[1], P[3], P[5], P[6], P[7], P[8], P[9], P[10], P[11], r->bias, r->head, r->w4dir);
     // backward image (tn_mlp_bwd.cuh): stage 0 = [W1 hi | W1 lo]; then per 128-wide layer [hi kb0 | hi kb1][lo kb0 | lo kb1]
     if (!r->wimg_bwd) TN_CUDA(cudaMalloc((void **)&r->wimg_bwd, BWD_WIMG_BYTES));
@@ -675,7 +697,7 @@ extern "C" int tn_render_set_weights(tn_tracer *h, const float *const *P, void *
     launch_pack_weights(P[2], 128, 0, 128, r->wimg_bwd + 1 * BWD_STAGE, s, 16384u, 32768u);
     launch_pack_weights(P[4], 128, 0, 128, r->wimg_bwd + 3 * BWD_STAGE, s, 16384u, 32768u);
     launch_pack_weights(P[6], 155, 27, 128, r->wimg_bwd + 5 * BWD_STAGE, s, 16384u, 32768u);
-    h->launches += 9;
+    h->launches += 13;
     TN_CUDA(cudaGetLastError());
     r->have_weights = true;
     return TN_OK;
@@ -712,11 +734,12 @@ static int render_impl(tn_tracer *h, const tn_render_config *cfg, const float *d
         if (rc) return rc;
     }
     r->train_valid = false;
+    const int prec = tf != nullptr ? 3 : r->mlp_prec;  // the training forward keeps bf16x3 (its backward recomputes in bf16x3)
     TN_CUDA(cudaMemsetAsync(r->n_active, 0, 16, s));
 #define TN_EV(i) do { if (r->profile) cudaEventRecord(r->ev[i], s); } while (0)
     TN_EV(0);  // the "trace" interval includes the L2 warm-up it exists for
     {   // L2 warm-up of everything read-only that the step gathers from (mesh tables, field shadow, weight image)
-        const void *extra[2] = {r->fshadow, r->wimg};
+        const void *extra[2] = {r->fshadow, prec == 2 ? r->wimg16 : r->wimg};
         const size_t extra_b[2] = {sizeof(float) * 64 * (size_t)r->V, 32768 + 3 * 65536};
         rc = launch_prefetch(h, extra, extra_b, 2, s);
         if (rc) return rc;
@@ -745,18 +768,20 @@ static int render_impl(tn_tracer *h, const tn_render_config *cfg, const float *d
     TN_CUDA(cudaFuncSetAttribute(k_sample_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
     TN_CUDA(cudaFuncSetAttribute(k_sample_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sf));
     TN_CUDA(cudaFuncSetAttribute(k_composite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    TN_CUDA(cudaFuncSetAttribute(k_mlp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
-    TN_CUDA(cudaFuncSetAttribute(k_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    auto k_coarse = prec == 2 ? k_mlp<false, 2> : k_mlp<false, 3>;
+    auto k_fine = prec == 2 ? k_mlp<true, 2> : k_mlp<true, 3>;
+    TN_CUDA(cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    TN_CUDA(cudaFuncSetAttribute(k_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
     const uint32_t gridR = (R + SAMPLE_WARPS - 1) / SAMPLE_WARPS;
 
     k_sample_coarse<<<gridR, SAMPLE_WARPS * 32, smem_sc, s>>>(p);
     TN_EV(2);
     MlpParams mc{};
-    mc.n_active = r->n_active; mc.S = Sc; mc.vi = r->vi_c; mc.bary = r->bary_c; mc.fshadow = r->fshadow; mc.wimg = r->wimg;
+    mc.n_active = r->n_active; mc.S = Sc; mc.vi = r->vi_c; mc.bary = r->bary_c; mc.fshadow = r->fshadow; mc.wimg = prec == 2 ? r->wimg16 : r->wimg;
     mc.bias = r->bias; mc.head = r->head; mc.dirbias = nullptr; mc.out = r->dens_c;
     mc.tile_ctr = r->n_active + 1;  // words 1, 2 of the zeroed 16-byte block: tile counters of the coarse / fine pass
     const uint32_t tiles_c = (uint32_t)(((uint64_t)R * Sc + 127) / 128), tiles_f = (uint32_t)(((uint64_t)R * S2 + 127) / 128);
-    if (!single) k_mlp<false><<<std::min<uint32_t>(tiles_c, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mc);
+    if (!single) k_coarse<<<std::min<uint32_t>(tiles_c, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mc);
     TN_EV(3);
     if (!single) k_sample_fine<<<gridR, SAMPLE_WARPS * 32, smem_sf, s>>>(p);
     else k_dirbias_only<<<gridR, SAMPLE_WARPS * 32, 0, s>>>(p);
@@ -767,7 +792,7 @@ static int render_impl(tn_tracer *h, const tn_render_config *cfg, const float *d
     else p.ebins_f = r->ebins_c;  // k_composite integrates over the coarse bins
     mf.timeline = g_timeline;
     mf.tile_ctr = r->n_active + 2;
-    k_mlp<true><<<std::min<uint32_t>(tiles_f, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mf);
+    k_fine<<<std::min<uint32_t>(tiles_f, (uint32_t)sms), MLP_THREADS, MLP_SMEM_BYTES, s>>>(mf);
     TN_EV(5);
     k_composite<<<gridR, SAMPLE_WARPS * 32, smem_c, s>>>(p);
     TN_EV(6);

@@ -156,6 +156,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
            | ((N >> 3) << 17)   // N / 8
            | ((M >> 4) << 24);  // M / 16
 }
+// the same for fp16 operands (format code 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // shared-memory matrix descriptor: K-major operand stored as [rows][64 bf16] (128-byte rows) with the
 // 128-byte swizzle; 8-row groups are 1024 bytes apart (SBO); version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -215,6 +219,13 @@ __device__ __forceinline__ void split_pack2(float e0, float e1, uint32_t &hi, ui
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(d1), "f"(d0));
     hi = h;
     lo = l;
+}
+
+// two floats -> packed fp16 pair (e0 in the low half)
+__device__ __forceinline__ uint32_t pack2_f16(float e0, float e1) {
+    uint32_t h;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(e1), "f"(e0));
+    return h;
 }
 
 // byte offset of element (n, k) inside a [rows][64] bf16 block stored with the 128-byte swizzle

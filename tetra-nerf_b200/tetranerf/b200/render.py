@@ -28,6 +28,7 @@ _lib.tn_render_train_forward.argtypes = [_vp, C.POINTER(_Cfg), _vp, _vp, C.c_uin
 _lib.tn_render_train_backward.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.POINTER(_vp), _vp]
 _lib.tn_render_debug_buffers.argtypes = [_vp, C.POINTER(_vp)]
 _lib.tn_render_set_profiling.argtypes = [_vp, C.c_int]
+_lib.tn_render_set_mlp_precision.argtypes = [_vp, C.c_int]
 _lib.tn_render_get_timings.argtypes = [_vp, C.POINTER(C.c_float)]
 _lib.tn_render_get_backward_timings.argtypes = [_vp, C.POINTER(C.c_float)]
 KERNEL_NAMES = ["trace", "sample_coarse", "mlp_coarse", "sample_fine", "mlp_fine", "composite"]
@@ -141,6 +142,11 @@ class FusedRenderer:
         ext._check(_lib.tn_render_train_backward(self.tracer.handle, grad_rgb.data_ptr(), grad_acc.data_ptr() if grad_acc is not None else None,
                                                  int(use_gradient_scaling), gfield.data_ptr(), arr, self._stream()))
         return gfield, dict(zip(PARAM_ORDER, gps))
+
+    def set_mlp_precision(self, prec: int) -> None:
+        """operand precision of the inference MLP: 2 = f16w2 (default: fp16 activations x fp16 hi/lo weights, ~2.6e-5 absolute on
+        unit-scale density / colour, inside the 1e-4 per-sample bar), 3 = bf16x3 (fp32-level, ~5e-7).  Training always runs bf16x3."""
+        ext._check(_lib.tn_render_set_mlp_precision(self.tracer.handle, int(prec)))
 
     def set_profiling(self, enable: bool) -> None:
         ext._check(_lib.tn_render_set_profiling(self.tracer.handle, int(enable)))
