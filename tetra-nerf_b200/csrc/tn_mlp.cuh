@@ -9,11 +9,11 @@
 // One persistent CTA per SM, 24 warps in six warpgroups with per-role register budgets (setmaxnreg):
 //   warps 0..15  : epilogue workers, two "slots" of 8 warps.  A slot owns one 128-sample tile at a time; warp (q,h)
 //                  of a slot owns sample rows 32q..32q+31 (its TMEM lane quarter, q = warp_id % 4) and the column
-//                  half h.  For each layer it waits for the accumulator, applies bias + ReLU to its 64 columns, splits
-//                  the result into bf16 hi/lo and writes the next A operand back into TMEM (activations never touch
-//                  shared or global memory); the last layer's epilogue also forms the head dot products.
+//                  half h.  For each layer it waits for the accumulator, applies bias + ReLU to its 64 columns, converts
+//                  the result (bf16 hi/lo pair, or one fp16 value) and writes the next A operand back into TMEM (activations
+//                  never touch shared or global memory); the last layer's epilogue also forms the head dot products.
 //   warp 16      : TMEM allocation, TMA bulk staging of the resident weight image, and (FINE) the producer of the
-//                  2-stage TMA ring that streams the 4th layer's weights in 16 KB (128 output rows x 64 K) chunks
+//                  2-stage (f16w2: 3-stage) TMA ring that streams the 4th layer's weights in 16 KB (128 output rows x 64 K) chunks
 //   warp 17      : issues every tcgen05.mma (one elected lane), strictly alternating between the two slots, which run
 //                  half a tile apart: one slot's epilogue overlaps the other slot's MMAs
 //   warps 20..23 : gather warps.  They run AHEAD of the slots: tile after tile they fetch the four vertex rows of
@@ -22,10 +22,13 @@
 //                  as the layer-0 A operand in shared memory (K-major, 128-byte swizzle), so the L2 latency of the
 //                  gather hides under the MMAs and epilogues of the previous tiles.  Layer 0 is an SS MMA (A and B
 //                  from shared memory), layers 1.. are TS MMAs (A from TMEM).
-// Products are "bf16x3": a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation in TMEM
-// (measured 5e-6 relative on B200, tests/test_gpu_mlp.py) -- the reference computes in fp32 and the
-// parity bar is 1e-4 absolute on colour/density, which single-pass bf16/tf32 cannot hold.
-// TMEM (512 columns): slot s uses [256s, 256s+128) for D, [+128,+192) A_hi, [+192,+256) A_lo.
+// Products: two operand precisions, template parameter PREC (see mlp_ring_stages below for the full note).
+//   PREC 3 "bf16x3": a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, bf16 halves, fp32 accumulation in TMEM (measured 5e-6 relative on B200,
+//           tests/test_gpu_mlp.py) -- the reference computes in fp32 and the parity bar is 1e-4 absolute on colour/density, which
+//           single-pass bf16/tf32 cannot hold.  Training forward.
+//   PREC 2 "f16w2":  a*(w_hi + w_lo) with ONE fp16 activation value and fp16 hi/lo weights (2.8e-5 absolute per sample on unit-scale
+//           outputs, tests/test_gpu_render.py) -- the inference default.
+// TMEM (512 columns): slot s uses [256s, 256s+128) for D, [+128,+192) A (hi), [+192,+256) A_lo (bf16x3 only).
 #pragma once
 #include "tn_common.cuh"
 #include "tn_tc.cuh"
