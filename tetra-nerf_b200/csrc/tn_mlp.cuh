@@ -36,6 +36,9 @@
 #ifndef TN_MLP_STATS
 #define TN_MLP_STATS 0   // 1: the gather warps also accumulate busy / wait cycles into the debug timeline (costs registers)
 #endif
+#ifndef TN_MLP_F16_WIDE
+#define TN_MLP_F16_WIDE 1   // f16w2 epilogue with two 32-column TMEM loads per warp instead of four 16-column ones
+#endif
 #ifndef TN_MLP_GATHER_ON
 #define TN_MLP_GATHER_ON true
 #endif
@@ -162,6 +165,47 @@ __device__ __forceinline__ void layer_epilogue(uint32_t d_t, uint32_t ahi, uint3
         if (KIND == 0) {
             tmem_st8(ahi + (col0 >> 1), ph);
             if (PREC != 2) tmem_st8(alo + (col0 >> 1), pl);
+        }
+    }
+    if (KIND == 2 || (KIND == 0 && dens)) acc.x = dsum.x + dsum.y;
+    if (KIND == 3) { acc.y = c0.x + c0.y; acc.z = c1.x + c1.y; acc.w = c2.x + c2.y; }
+}
+// f16w2 form of the epilogue: the conversion is four instructions per pair, so what the epilogue waits for is TMEM -- the in-kernel
+// timeline put an epilogue at 1.7-3.3k cycles, mostly the four load round trips (~230 cycles each under the other slot's MMAs).  Here the
+// warp's 64 columns come in TWO loads of 32 columns, the second in flight while the first is processed; the biases are read on the
+// fly (L1).  64 data registers: possible because this mode keeps no lo halves.
+template <int KIND>
+__device__ __forceinline__ void layer_epilogue_f16(uint32_t d_t, uint32_t ahi, uint32_t h, const float *__restrict__ bias128, bool dens,
+                                                   const float *__restrict__ wd, const float *__restrict__ wc, float4 &acc) {
+    using namespace tc;
+    float2 dsum = make_float2(0.f, 0.f), c0 = dsum, c1 = dsum, c2 = dsum;
+    uint32_t ra[32], rb[32];
+    tmem_ld32(d_t + h * 64u, ra);
+    tmem_ld_wait();
+    tmem_ld32(d_t + h * 64u + 32u, rb);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1) tmem_ld_wait();
+        const uint32_t *r = half ? rb : ra;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {  // 16 columns -> 8 packed words -> one tcgen05.st
+            const uint32_t col0 = h * 64u + half * 32u + g * 16u;
+            uint32_t ph[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 b = __ldg(reinterpret_cast<const float2 *>(bias128 + col0 + 2 * i));
+                float2 x = add2(make_float2(__uint_as_float(r[g * 16 + 2 * i]), __uint_as_float(r[g * 16 + 2 * i + 1])), b);
+                x.x = fmaxf(x.x, 0.f);
+                x.y = fmaxf(x.y, 0.f);
+                if (KIND == 0) ph[i] = pack2_f16(x.x, x.y);
+                if (KIND == 2 || (KIND == 0 && dens)) dsum = fma2(x, *reinterpret_cast<const float2 *>(wd + col0 + 2 * i), dsum);
+                if (KIND == 3) {
+                    c0 = fma2(x, *reinterpret_cast<const float2 *>(wc + col0 + 2 * i), c0);
+                    c1 = fma2(x, *reinterpret_cast<const float2 *>(wc + 128 + col0 + 2 * i), c1);
+                    c2 = fma2(x, *reinterpret_cast<const float2 *>(wc + 256 + col0 + 2 * i), c2);
+                }
+            }
+            if (KIND == 0) tmem_st8(ahi + (col0 >> 1), ph);
         }
     }
     if (KIND == 2 || (KIND == 0 && dens)) acc.x = dsum.x + dsum.y;
@@ -570,7 +614,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
             const float *bias4 = nullptr;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             float2 bpre[8];
-            bias_prefetch(p.bias, h, bpre);  // layer 0: known before the tile is
+            if (!(PREC == 2 && TN_MLP_F16_WIDE)) bias_prefetch(p.bias, h, bpre);  // layer 0: known before the tile is
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
                 tl_mark(p.timeline, lane, warp, 7, n, l);  // ev 7: start waiting for D
@@ -586,13 +630,18 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(const MlpParams p) {
                     if (FINE) bias4 = p.dirbias + (size_t)(min(my_row, total_rows - 1) / p.S) * 128;  // per-ray direction bias of this thread's row
                 }
                 if (l < L - 1) {
-                    layer_epilogue<0, PREC>(d_t, ahi, alo, h, p.bias + l * 128, bpre, FINE && l == 2, wd, wc, acc);
-                    // the next layer's first bias chunk: in flight while the next GEMM runs
-                    if (FINE && l == 2) bias_prefetch(bias4, h, bpre); else bias_prefetch(p.bias + (l + 1) * 128, h, bpre);
+                    if (PREC == 2 && TN_MLP_F16_WIDE) layer_epilogue_f16<0>(d_t, ahi, h, p.bias + l * 128, FINE && l == 2, wd, wc, acc);
+                    else {
+                        layer_epilogue<0, PREC>(d_t, ahi, alo, h, p.bias + l * 128, bpre, FINE && l == 2, wd, wc, acc);
+                        // the next layer's first bias chunk: in flight while the next GEMM runs
+                        if (FINE && l == 2) bias_prefetch(bias4, h, bpre); else bias_prefetch(p.bias + (l + 1) * 128, h, bpre);
+                    }
                 } else if (FINE) {
-                    layer_epilogue<3, PREC>(d_t, ahi, alo, h, bias4, bpre, false, wd, wc, acc);
+                    if (PREC == 2 && TN_MLP_F16_WIDE) layer_epilogue_f16<3>(d_t, ahi, h, bias4, false, wd, wc, acc);
+                    else layer_epilogue<3, PREC>(d_t, ahi, alo, h, bias4, bpre, false, wd, wc, acc);
                 } else {
-                    layer_epilogue<2, PREC>(d_t, ahi, alo, h, p.bias + 256, bpre, false, wd, wc, acc);
+                    if (PREC == 2 && TN_MLP_F16_WIDE) layer_epilogue_f16<2>(d_t, ahi, h, p.bias + 256, false, wd, wc, acc);
+                    else layer_epilogue<2, PREC>(d_t, ahi, alo, h, p.bias + 256, bpre, false, wd, wc, acc);
                 }
                 // next A operand written (l < L-1) / accumulator read out and free for the next tile (l == L-1)
                 if (l < L - 1) tmem_st_wait();
