@@ -154,3 +154,18 @@ def test_fused_render_is_deterministic_and_reusable(small_mesh):
     c = fr.render(torch.from_numpy(o[:100]).to(DEV), torch.from_numpy(d[:100]).to(DEV), st)
     tr.synchronize()
     assert torch.equal(c["rgb"], a["rgb"][:100])
+
+
+def test_f16w2_saturates_out_of_range_activations(small_mesh):
+    """the f16w2 mode carries activations as fp16: features beyond +-65504 must saturate (not turn into inf / NaN pixels);
+    bf16x3 covers the fp32 range and stays the reference for such fields"""
+    from tetranerf.b200.render import RenderSettings
+
+    V, C = small_mesh
+    tr, fr, field, params = setup(V, C, prec=2)
+    fr.set_field(torch.from_numpy(field * 3.0e5).to(DEV))
+    o, d = syn.camera_rays(128, seed=4)
+    out = fr.render(torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), RenderSettings.tetra_nerf())
+    tr.synchronize()
+    for k in ("rgb", "accumulation", "depth"):
+        assert bool(torch.isfinite(out[k]).all()), k

@@ -23,7 +23,7 @@ static __global__ void k_pack_weights(const float *__restrict__ W, uint32_t row_
     const uint32_t kb = k >> 6, kk = k & 63u;
     const uint32_t off = kb * kb_stride + tc::sw128_offset(n, kk);
     if (fp16) {
-        const __half hi = __float2half_rn(w);
+        const __half hi = __float2half_rn(fminf(fmaxf(w, -65504.0f), 65504.0f));  // saturate (a weight that large has left fp16 anyway)
         const __half lo = __float2half_rn(w - __half2float(hi));
         *reinterpret_cast<__half *>(img + off) = hi;
         *reinterpret_cast<__half *>(img + off + lo_off) = lo;

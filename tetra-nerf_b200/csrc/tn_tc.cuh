@@ -221,10 +221,11 @@ __device__ __forceinline__ void split_pack2(float e0, float e1, uint32_t &hi, ui
     lo = l;
 }
 
-// two floats -> packed fp16 pair (e0 in the low half)
+// two floats -> packed fp16 pair (e0 in the low half); values beyond the fp16 range saturate to +-65504 instead of becoming inf
+// (an activation that large would otherwise turn the whole accumulator row into inf / NaN)
 __device__ __forceinline__ uint32_t pack2_f16(float e0, float e1) {
     uint32_t h;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(e1), "f"(e0));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(e1), "f"(e0));
     return h;
 }
 
