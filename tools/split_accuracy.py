@@ -57,22 +57,29 @@ def mlp(scheme):
     return sigma, rgb
 
 
-ref_s, ref_c = mlp(None)
 bf, fp = torch.bfloat16, torch.float16
-schemes = {
-    "bf16x3 (shipped): hi.hi + lo.hi + hi.lo": (bf, [(0, 0), (1, 0), (0, 1)]),
+SCHEMES = {
+    "bf16x3 (training / reference mode): hi.hi + lo.hi + hi.lo": (bf, [(0, 0), (1, 0), (0, 1)]),
     "fp16x3: hi.hi + lo.hi + hi.lo": (fp, [(0, 0), (1, 0), (0, 1)]),
     "fp16x2: (a_hi + a_lo).w_hi": (fp, [(0, 0), (1, 0)]),
-    "fp16x2: a_hi.(w_hi + w_lo)": (fp, [(0, 0), (0, 1)]),
+    "f16w2 (inference default): a_hi.(w_hi + w_lo)": (fp, [(0, 0), (0, 1)]),
     "bf16x2: (a_hi + a_lo).w_hi": (bf, [(0, 0), (1, 0)]),
     "fp16x1": (fp, [(0, 0)]),
 }
-print(f"{N} samples; max / 99.9th-percentile absolute error against float64 (bar: 1e-4 per sample)")
-for name, sc in schemes.items():
-    s, c = mlp(sc)
-    es = (s - ref_s).abs().flatten()
-    line = f"{name:44s} sigma {es.max().item():.2e} / {es.quantile(0.999).item():.2e}"
-    if c is not None:
-        ec = (c - ref_c).abs().flatten()
-        line += f"   colour {ec.max().item():.2e} / {ec.quantile(0.999).item():.2e}"
-    print(line)
+
+
+def errors():
+    """{scheme: (max |sigma err|, max |colour err|)} against float64"""
+    ref_s, ref_c = mlp(None)
+    out = {}
+    for name, sc in SCHEMES.items():
+        s, c = mlp(sc)
+        out[name] = ((s - ref_s).abs().max().item(), (c - ref_c).abs().max().item(),
+                     (s - ref_s).abs().flatten().quantile(0.999).item(), (c - ref_c).abs().flatten().quantile(0.999).item())
+    return out
+
+
+if __name__ == "__main__":
+    print(f"{N} samples; max / 99.9th-percentile absolute error against float64 (bar: 1e-4 per sample)")
+    for name, (es, ec, qs, qc) in errors().items():
+        print(f"{name:58s} sigma {es:.2e} / {qs:.2e}   colour {ec:.2e} / {qc:.2e}")
